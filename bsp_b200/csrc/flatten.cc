@@ -1,0 +1,200 @@
+/*
+ * flatten.cc -- raw IBSP lumps -> validated, flattened device image (see map_layout.h).
+ *
+ * Follows what the reference reads on the trace path: node.plane / node.children
+ * (bsp.cc:214-215,248-251), leaf.first_brush / num_brushes (bsp.cc:188), leaf_brushes[]
+ * (bsp.cc:189), brush.texture -> texture.content_flags & 1 (bsp.cc:190-193),
+ * brush.first_side / num_sides -> side.plane -> plane (bsp.cc:127-129).
+ * The reference performs no bounds checks on any of these; here every index is checked
+ * once so the kernels do not have to.
+ */
+#include "flatten.h"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace bspk {
+
+namespace {
+
+/* on-disk Q3 IBSP v46 records (reference bsp.h:41-96) */
+#pragma pack( push, 1 )
+struct DiskTexture { char name[ 64 ]; int32_t surface_flags; int32_t content_flags; };
+struct DiskPlane { float n[ 3 ]; float d; };
+struct DiskNode { uint32_t plane; int32_t children[ 2 ]; int32_t mins[ 3 ]; int32_t maxs[ 3 ]; };
+struct DiskLeaf { int32_t cluster, area; int32_t mins[ 3 ], maxs[ 3 ]; uint32_t first_face, num_faces, first_brush, num_brushes; };
+struct DiskBrush { uint32_t first_side, num_sides; int32_t texture; };
+struct DiskSide { uint32_t plane; int32_t texture; };
+#pragma pack( pop )
+
+static_assert( sizeof( DiskTexture ) == 72, "texture" );
+static_assert( sizeof( DiskPlane ) == 16, "plane" );
+static_assert( sizeof( DiskNode ) == 36, "node" );
+static_assert( sizeof( DiskLeaf ) == 48, "leaf" );
+static_assert( sizeof( DiskBrush ) == 12, "brush" );
+static_assert( sizeof( DiskSide ) == 8, "side" );
+
+const int kSolidBit = 1; /* the reference's "magic number", bsp.cc:192-193 */
+
+uint64_t align_up( uint64_t v, uint64_t a ) { return ( v + a - 1 ) / a * a; }
+
+std::string fmt( const char * f, long long a = 0, long long b = 0, long long c = 0 ) {
+	char buf[ 256 ];
+	snprintf( buf, sizeof( buf ), f, a, b, c );
+	return buf;
+}
+
+} // namespace
+
+int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
+	if( L.num_nodes == 0 || !L.nodes ) { err = "map has no nodes (the trace starts at node 0, bsp.cc:263)"; return BSPGPU_E_MAP; }
+	if( ( L.num_planes && !L.planes ) || ( L.num_leaves && !L.leaves ) || ( L.num_brushes && !L.brushes ) ||
+	    ( L.num_brush_sides && !L.brush_sides ) || ( L.num_leaf_brushes && !L.leaf_brushes ) || ( L.num_textures && !L.textures ) ) {
+		err = "null lump pointer with non-zero count"; return BSPGPU_E_INVALID;
+	}
+	const DiskTexture * textures = ( const DiskTexture * ) L.textures;
+	const DiskPlane * planes = ( const DiskPlane * ) L.planes;
+	const DiskNode * nodes = ( const DiskNode * ) L.nodes;
+	const DiskLeaf * leaves = ( const DiskLeaf * ) L.leaves;
+	const uint32_t * leaf_brushes = ( const uint32_t * ) L.leaf_brushes;
+	const DiskBrush * brushes = ( const DiskBrush * ) L.brushes;
+	const DiskSide * sides = ( const DiskSide * ) L.brush_sides;
+
+	/* ---- brushes: side ranges, side planes, texture index (checked for every brush a leaf can name) */
+	std::vector< uint8_t > brush_solid( L.num_brushes, 0 );
+	for( uint32_t b = 0; b < L.num_brushes; b++ ) {
+		const DiskBrush & br = brushes[ b ];
+		if( br.texture < 0 || ( uint32_t ) br.texture >= L.num_textures ) { err = fmt( "brush %lld: texture %lld out of range", b, br.texture ); return BSPGPU_E_MAP; }
+		if( ( uint64_t ) br.first_side + br.num_sides > L.num_brush_sides ) { err = fmt( "brush %lld: sides [%lld,+%lld) out of range", b, br.first_side, br.num_sides ); return BSPGPU_E_MAP; }
+		if( br.num_sides >= kLastRef ) { err = fmt( "brush %lld: too many sides", b ); return BSPGPU_E_MAP; }
+		brush_solid[ b ] = ( textures[ br.texture ].content_flags & kSolidBit ) ? 1 : 0;
+	}
+	for( uint32_t s = 0; s < L.num_brush_sides; s++ ) {
+		if( sides[ s ].plane >= L.num_planes ) { err = fmt( "brushside %lld: plane %lld out of range", s, sides[ s ].plane ); return BSPGPU_E_MAP; }
+	}
+
+	/* ---- walk the tree from node 0 breadth-first: validates children, rejects nodes reached twice
+	 *      (cycles would hang the reference too), assigns BFS indices, measures depth */
+	std::vector< int32_t > bfs_of( L.num_nodes, -1 );
+	std::vector< uint32_t > order;      /* BFS position -> file node index */
+	std::vector< uint32_t > depth_of;   /* per BFS position */
+	order.reserve( L.num_nodes ); depth_of.reserve( L.num_nodes );
+	order.push_back( 0 ); depth_of.push_back( 1 ); bfs_of[ 0 ] = 0;
+	uint32_t tree_depth = 1;
+	for( size_t head = 0; head < order.size(); head++ ) {
+		const uint32_t ni = order[ head ];
+		const DiskNode & nd = nodes[ ni ];
+		if( nd.plane >= L.num_planes ) { err = fmt( "node %lld: plane %lld out of range", ni, nd.plane ); return BSPGPU_E_MAP; }
+		for( int k = 0; k < 2; k++ ) {
+			const int32_t c = nd.children[ k ];
+			if( c >= 0 ) {
+				if( ( uint32_t ) c >= L.num_nodes ) { err = fmt( "node %lld: child %lld out of range", ni, c ); return BSPGPU_E_MAP; }
+				if( bfs_of[ c ] != -1 ) { err = fmt( "node %lld reached twice (cycle or shared subtree) via node %lld", c, ni ); return BSPGPU_E_MAP; }
+				bfs_of[ c ] = ( int32_t ) order.size();
+				order.push_back( ( uint32_t ) c );
+				depth_of.push_back( depth_of[ head ] + 1 );
+				if( depth_of[ head ] + 1 > tree_depth ) tree_depth = depth_of[ head ] + 1;
+			}
+			else {
+				const int64_t leaf = -( ( int64_t ) c + 1 );
+				if( leaf >= ( int64_t ) L.num_leaves ) { err = fmt( "node %lld: leaf %lld out of range", ni, leaf ); return BSPGPU_E_MAP; }
+				const DiskLeaf & lf = leaves[ leaf ];
+				if( ( uint64_t ) lf.first_brush + lf.num_brushes > L.num_leaf_brushes ) { err = fmt( "leaf %lld: leafbrushes [%lld,+%lld) out of range", leaf, lf.first_brush, lf.num_brushes ); return BSPGPU_E_MAP; }
+				for( uint32_t i = 0; i < lf.num_brushes; i++ ) {
+					if( leaf_brushes[ lf.first_brush + i ] >= L.num_brushes ) { err = fmt( "leaf %lld: brush %lld out of range", leaf, leaf_brushes[ lf.first_brush + i ] ); return BSPGPU_E_MAP; }
+				}
+			}
+		}
+	}
+
+	/* ---- emit */
+	const uint32_t num_nodes = ( uint32_t ) order.size();
+	std::vector< NodeRec > onodes( num_nodes );
+	std::vector< BrushRef > orefs;
+	for( uint32_t i = 0; i < num_nodes; i++ ) {
+		const DiskNode & nd = nodes[ order[ i ] ];
+		const DiskPlane & pl = planes[ nd.plane ];
+		NodeRec & o = onodes[ i ];
+		o.nx = pl.n[ 0 ]; o.ny = pl.n[ 1 ]; o.nz = pl.n[ 2 ]; o.d = pl.d;
+		for( int k = 0; k < 2; k++ ) {
+			const int32_t c = nd.children[ k ];
+			o.orig_child[ k ] = c;
+			if( c >= 0 ) { o.child[ k ] = bfs_of[ c ]; continue; }
+			const DiskLeaf & lf = leaves[ -( ( int64_t ) c + 1 ) ];
+			const size_t first_ref = orefs.size();
+			for( uint32_t j = 0; j < lf.num_brushes; j++ ) {
+				const uint32_t b = leaf_brushes[ lf.first_brush + j ];
+				if( !brush_solid[ b ] ) continue;
+				BrushRef r;
+				r.first_side = brushes[ b ].first_side; r.num_sides = brushes[ b ].num_sides;
+				r.brush = ( int32_t ) b; r.reserved = 0;
+				orefs.push_back( r );
+			}
+			if( orefs.size() == first_ref ) { o.child[ k ] = kEmptyLeaf; continue; }
+			if( first_ref >= 0x7fffffffu ) { err = "too many leaf brush references"; return BSPGPU_E_MAP; }
+			orefs.back().num_sides |= kLastRef;
+			o.child[ k ] = ~( int32_t ) first_ref;
+		}
+	}
+
+	MapImageLayout & lay = out.layout;
+	lay.num_nodes = num_nodes; lay.num_refs = ( uint32_t ) orefs.size(); lay.num_sides = L.num_brush_sides;
+	lay.tree_depth = tree_depth;
+	lay.off_nodes = 0;
+	lay.off_refs = align_up( lay.off_nodes + ( uint64_t ) num_nodes * sizeof( NodeRec ), kSectionAlign );
+	lay.off_sides = align_up( lay.off_refs + ( uint64_t ) orefs.size() * sizeof( BrushRef ), kSectionAlign );
+	lay.staged_bytes = align_up( lay.off_sides + ( uint64_t ) L.num_brush_sides * sizeof( SideRec ), kSectionAlign );
+	lay.off_side_plane = lay.staged_bytes;
+	lay.total_bytes = align_up( lay.off_side_plane + ( uint64_t ) L.num_brush_sides * sizeof( uint32_t ), kSectionAlign );
+	if( lay.total_bytes == 0 ) lay.total_bytes = kSectionAlign;
+
+	out.image.assign( lay.total_bytes, 0 );
+	memcpy( out.image.data() + lay.off_nodes, onodes.data(), onodes.size() * sizeof( NodeRec ) );
+	if( !orefs.empty() ) memcpy( out.image.data() + lay.off_refs, orefs.data(), orefs.size() * sizeof( BrushRef ) );
+	SideRec * osides = ( SideRec * ) ( out.image.data() + lay.off_sides );
+	uint32_t * oside_plane = ( uint32_t * ) ( out.image.data() + lay.off_side_plane );
+	for( uint32_t s = 0; s < L.num_brush_sides; s++ ) {
+		const DiskPlane & pl = planes[ sides[ s ].plane ];
+		osides[ s ].nx = pl.n[ 0 ]; osides[ s ].ny = pl.n[ 1 ]; osides[ s ].nz = pl.n[ 2 ]; osides[ s ].d = pl.d;
+		oside_plane[ s ] = sides[ s ].plane;
+	}
+	return BSPGPU_OK;
+}
+
+int read_ibsp_file( const char * path, std::vector< unsigned char > & blob, bspgpu_map_desc & lumps, std::string & err ) {
+	FILE * f = fopen( path, "rb" );
+	if( !f ) { err = std::string( "cannot open " ) + path; return BSPGPU_E_IO; }
+	fseek( f, 0, SEEK_END );
+	const long len = ftell( f );
+	fseek( f, 0, SEEK_SET );
+	if( len < 8 + 8 * 17 ) { fclose( f ); err = "file shorter than an IBSP header"; return BSPGPU_E_IO; }
+	blob.resize( ( size_t ) len );
+	const size_t got = fread( blob.data(), 1, ( size_t ) len, f );
+	fclose( f );
+	if( got != ( size_t ) len ) { err = "short read"; return BSPGPU_E_IO; }
+
+	/* header: 4-byte magic, u32 version, then {off,len} per lump (reference bsp.h:29-39).  Like the
+	 * reference (bsp.cc:58-86) magic and version are not checked; lump slots 1,2,3,4,6,8,9 are used. */
+	struct Dirent { uint32_t off, len; };
+	const Dirent * dir = ( const Dirent * ) ( blob.data() + 8 );
+	struct Want { int slot; size_t elem; const void ** ptr; uint32_t * count; const char * name; };
+	const Want wants[] = {
+		{ 1, sizeof( DiskTexture ), &lumps.textures, &lumps.num_textures, "textures" },
+		{ 2, sizeof( DiskPlane ), &lumps.planes, &lumps.num_planes, "planes" },
+		{ 3, sizeof( DiskNode ), &lumps.nodes, &lumps.num_nodes, "nodes" },
+		{ 4, sizeof( DiskLeaf ), &lumps.leaves, &lumps.num_leaves, "leaves" },
+		{ 6, sizeof( uint32_t ), &lumps.leaf_brushes, &lumps.num_leaf_brushes, "leafbrushes" },
+		{ 8, sizeof( DiskBrush ), &lumps.brushes, &lumps.num_brushes, "brushes" },
+		{ 9, sizeof( DiskSide ), &lumps.brush_sides, &lumps.num_brush_sides, "brushsides" },
+	};
+	for( const Want & w : wants ) {
+		const Dirent & d = dir[ w.slot ];
+		if( d.len % w.elem != 0 ) { err = std::string( w.name ) + ": lump length not a multiple of the record size (bsp.cc:97)"; return BSPGPU_E_MAP; }
+		if( ( uint64_t ) d.off + d.len > ( uint64_t ) len ) { err = std::string( w.name ) + ": lump runs past end of file"; return BSPGPU_E_MAP; }
+		*w.ptr = blob.data() + d.off;
+		*w.count = ( uint32_t ) ( d.len / w.elem );
+	}
+	return BSPGPU_OK;
+}
+
+} // namespace bspk

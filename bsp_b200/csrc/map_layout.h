@@ -1,0 +1,60 @@
+/*
+ * map_layout.h -- the flattened device image of a BSP map (shared by host and device code).
+ *
+ * The reference walks AoS file lumps: node -> plane, leaf -> leafbrush -> brush -> texture,
+ * brush -> brushside -> plane (reference bsp.cc:127-129,186-190,214-215), using 12 of 36,
+ * 8 of 48 and 4 of 72 bytes of the records it touches.  The device image keeps only what
+ * the trace reads and removes every second hop:
+ *
+ *   NodeRec  (32 B)  split plane embedded + both children; nodes in breadth-first order so
+ *                    the top of the tree is one contiguous prefix (staged in shared memory).
+ *                    child >= 0: node index; child == kEmptyLeaf: leaf without solid brushes;
+ *                    otherwise ~child = index of the leaf's first BrushRef.
+ *   BrushRef (16 B)  one per (leaf, solid brush): side range + brush index; the leaf's last
+ *                    entry carries kLastRef, so no leaf record and no count are needed.
+ *                    The content test (textures[brush.texture].content_flags & 1, bsp.cc:193)
+ *                    is baked in: non-solid brushes are dropped at flatten time.
+ *   SideRec  (16 B)  the side's plane embedded (n.xyz, d), indexed like the brushsides lump.
+ *   side_plane (4 B) planes-lump index per side, read once per hit for the `plane` extension.
+ *
+ * One device allocation holds [nodes | refs | sides | side_plane], each section 128-byte
+ * aligned; the whole-map shared-memory variant copies the first three sections verbatim.
+ */
+#ifndef BSPGPU_MAP_LAYOUT_H
+#define BSPGPU_MAP_LAYOUT_H
+
+#include <stdint.h>
+
+namespace bspk {
+
+struct alignas( 16 ) NodeRec {
+	float nx, ny, nz, d;
+	int32_t child[ 2 ];      /* [0] front (dist >= 0 side), [1] back -- same slot order as the reference */
+	int32_t orig_child[ 2 ]; /* the file's own child values (leaf = -(idx+1)), for position_to_leaf */
+};
+
+struct alignas( 16 ) BrushRef {
+	uint32_t first_side;
+	uint32_t num_sides;      /* bit 31 (kLastRef) = last solid brush of this leaf */
+	int32_t brush;           /* brushes-lump index */
+	uint32_t reserved;
+};
+
+struct alignas( 16 ) SideRec {
+	float nx, ny, nz, d;
+};
+
+static const int32_t kEmptyLeaf = INT32_MIN;
+static const uint32_t kLastRef = 0x80000000u;
+static const uint32_t kSectionAlign = 128;
+
+/* byte offsets of the sections inside the single device image */
+struct MapImageLayout {
+	uint32_t num_nodes, num_refs, num_sides, tree_depth;
+	uint64_t off_nodes, off_refs, off_sides, off_side_plane, total_bytes;
+	uint64_t staged_bytes;   /* prefix [nodes|refs|sides] the whole-map variant copies to shared memory */
+};
+
+} // namespace bspk
+
+#endif

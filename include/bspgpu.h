@@ -1,0 +1,167 @@
+/*
+ * bspgpu.h -- C ABI of the B200 batched BSP segment tracer (libbspgpu.so).
+ *
+ * This is the drop-in boundary for ONE path of mikejsavage/bsp: the per-call CPU
+ * segment trace  BSP::trace_seg -> trace_seg_tree -> trace_seg_leaf -> trace_seg_brush
+ * (reference bsp.cc:120-271, declared bsp.h:203-210).  The reference has no FFI of
+ * its own (C++ only); each entry point below names the reference interface it
+ * replaces or extends.  Plain pointers and sizes only -- no CUDA, torch or C++
+ * types cross this boundary.
+ *
+ * Threading: calls on one handle are serialised on the handle's stream and, unless
+ * BSPGPU_ASYNC is passed, synchronous on return.  Different handles are independent.
+ * Errors: every int-returning call gives 0 on success or a negative BSPGPU_E_* code;
+ * bspgpu_last_error() then returns a thread-local message.  There is no CPU fallback:
+ * without a usable sm_100 device every compute call fails with BSPGPU_E_CUDA.
+ */
+#ifndef BSPGPU_H
+#define BSPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSPGPU_ABI_VERSION 1
+
+enum {
+	BSPGPU_OK = 0,
+	BSPGPU_E_INVALID = -1,   /* bad argument */
+	BSPGPU_E_MAP = -2,       /* map failed validation (index out of range, cycle, too deep ...) */
+	BSPGPU_E_CUDA = -3,      /* CUDA runtime error / no device */
+	BSPGPU_E_IO = -4,        /* file could not be read */
+	BSPGPU_E_NOMEM = -5
+};
+
+typedef struct bspgpu bspgpu_t;
+
+/* The seven lumps the trace reads, exactly as bsp_init leaves them in the BSP object
+ * (reference bsp.cc:74-81 / bsp.h:160-182): pointers into the file blob + counts.
+ * Element layouts are the on-disk Q3 IBSP v46 structs (bsp.h:41-96):
+ * texture 72 B, plane 16 B, node 36 B, leaf 48 B, leafbrush 4 B, brush 12 B, brushside 8 B. */
+typedef struct bspgpu_map_desc {
+	const void * textures;     uint32_t num_textures;
+	const void * planes;       uint32_t num_planes;
+	const void * nodes;        uint32_t num_nodes;
+	const void * leaves;       uint32_t num_leaves;
+	const void * leaf_brushes; uint32_t num_leaf_brushes;
+	const void * brushes;      uint32_t num_brushes;
+	const void * brush_sides;  uint32_t num_brush_sides;
+} bspgpu_map_desc;
+
+/* One segment = the (start, end) argument pair of BSP::trace_seg (bsp.h:210), padded to
+ * two float4 so a warp loads it with coalesced 16-byte accesses.  The pads are ignored. */
+typedef struct bspgpu_segment {
+	float start[ 3 ]; float pad0;
+	float end[ 3 ];   float pad1;
+} bspgpu_segment;
+
+/* One result = the outputs of BSP::trace_seg (bool return + Intersection, bsp.h:143-147).
+ *   flags bit0 (BSPGPU_HIT)  == the reference's return value                 [reference parity]
+ *   t                        == Intersection::t (1.0f on a miss)             [reference parity]
+ *   plane, brush, BSPGPU_STARTSOLID are EXTENSIONS with no reference ground truth (the
+ *   reference never assigns Intersection::plane and has no startsolid output); they are
+ *   defined by oracle/restate.c:
+ *     plane = planes-lump index of the side that last raised tfar in the brush that supplied
+ *             t (first brush in leaf order on exact ties), -1 on a miss or when the hit was
+ *             reported at the interval start without any side raising tfar;
+ *     brush = brushes-lump index of that brush, -1 on a miss;
+ *     STARTSOLID = some tested solid brush had the segment start on/behind all of its sides.
+ * Intersection::pos is start + t*(end-start) on a hit, (0,0,0) on a miss: written to the
+ * optional pos array of bspgpu_trace_pos. */
+typedef struct bspgpu_result {
+	float t;
+	int32_t plane;
+	int32_t brush;
+	uint32_t flags;
+} bspgpu_result;
+
+#define BSPGPU_HIT        1u
+#define BSPGPU_STARTSOLID 2u
+
+/* {pos.xyz, t}: Intersection::pos and ::t as one float4 */
+typedef struct bspgpu_pos { float pos[ 3 ]; float t; } bspgpu_pos;
+
+/* bspgpu_trace flags */
+#define BSPGPU_SEGS_DEVICE   0x01u  /* segs is a device pointer (already resident in HBM) */
+#define BSPGPU_OUT_DEVICE    0x02u  /* out / pos are device pointers */
+#define BSPGPU_SEGS_PACKED24 0x04u  /* segs are 6 floats each (two glm::vec3, the reference's own argument layout) */
+#define BSPGPU_ASYNC         0x08u  /* device pointers only: enqueue on the handle's stream and return */
+
+/* kernel variant override for bspgpu_set_option(BSPGPU_OPT_VARIANT): default AUTO */
+enum {
+	BSPGPU_VARIANT_AUTO = 0,
+	BSPGPU_VARIANT_SMEM = 1,     /* whole flattened map staged in shared memory (fails if it does not fit) */
+	BSPGPU_VARIANT_TOPTREE = 2,  /* top of the tree in shared memory, rest read-only through L1/L2 */
+	BSPGPU_VARIANT_GLOBAL = 3    /* nothing staged */
+};
+enum {
+	BSPGPU_OPT_VARIANT = 1,
+	BSPGPU_OPT_BLOCK_THREADS = 2,   /* threads per CTA (multiple of 32) */
+	BSPGPU_OPT_CTAS_PER_SM = 3,
+	BSPGPU_OPT_TOPTREE_BYTES = 4,   /* shared-memory budget of the TOPTREE variant */
+	BSPGPU_OPT_CHUNK_SEGMENTS = 5,  /* host-pointer path: segments per pipelined H2D/kernel/D2H chunk */
+	BSPGPU_OPT_REFILL = 6           /* persistent-warp refill threshold (idle lanes before a warp fetches work) */
+};
+
+typedef struct bspgpu_info {
+	uint32_t abi_version;
+	int32_t device;
+	uint32_t sm_count;
+	uint32_t variant;            /* variant the last trace ran */
+	uint32_t block_threads, grid_ctas;
+	uint32_t smem_bytes;         /* dynamic shared memory per CTA of the last trace */
+	uint32_t tree_depth;         /* deepest node chain of the flattened tree */
+	uint32_t num_nodes, num_brush_refs, num_sides;  /* flattened (reachable, solid-only) counts */
+	uint64_t map_bytes;          /* flattened device image size */
+	float last_kernel_ms;        /* CUDA-event time of the last trace's kernel(s) on the handle's stream */
+	uint32_t last_launches;      /* kernels launched by the last call */
+} bspgpu_info;
+
+/* ---- lifetime (replaces nothing: the reference keeps the map in host memory; this COPIES and
+ *      flattens it into device buffers, the caller's lumps may be freed afterwards) ---- */
+int bspgpu_create( bspgpu_t ** out, const bspgpu_map_desc * lumps, int device );
+/* convenience: read an IBSP file the way bsp_init does (bsp.cc:58-86; 17- or 18-slot header) */
+int bspgpu_create_from_file( bspgpu_t ** out, const char * path, int device );
+void bspgpu_destroy( bspgpu_t * h );
+
+/* ---- the hot path: n x BSP::trace_seg (bsp.cc:255-271) ---- */
+int bspgpu_trace( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result * out, unsigned flags );
+/* same, also writing Intersection::pos (bsp.cc:265-267); out or pos may be NULL (not both) */
+int bspgpu_trace_pos( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result * out, bspgpu_pos * pos, unsigned flags );
+/* number of hits of the last completed trace on this handle (device-side reduction) */
+int bspgpu_hit_count( bspgpu_t * h, uint64_t * hits );
+
+/* ---- batched BSP::position_to_leaf (bsp.cc:273-286): pts = 3 floats each (stride in floats), leaf = leaves-lump index ---- */
+int bspgpu_leaf( bspgpu_t * h, const float * pts, uint32_t stride, uint64_t n, int32_t * leaf, unsigned flags );
+
+/* ---- synthetic workload generator (tools/seggen.py, bit-identical): writes `count` device segments ---- */
+typedef struct bspgpu_gen_desc {
+	uint32_t kind;            /* 0 uniform, 1 long (isotropic direction, length range), 2 camera grid */
+	uint64_t seed;
+	float lo[ 3 ], hi[ 3 ];   /* box for start points (and end points when kind==0) */
+	float len_lo, len_hi;     /* kind 1 */
+	const float * views;      /* kind 2: host array, 12 floats per view {eye, fwd, right, up} */
+	uint32_t num_views, width, height;
+	float tan_half, far_dist;
+} bspgpu_gen_desc;
+int bspgpu_generate( bspgpu_t * h, const bspgpu_gen_desc * g, uint64_t first, uint64_t count, void * dev_segs );
+
+/* ---- plumbing ---- */
+int bspgpu_set_option( bspgpu_t * h, int option, int64_t value );
+int bspgpu_set_stream( bspgpu_t * h, void * cuda_stream );  /* run on a caller-owned cudaStream_t (NULL = handle's own) */
+int bspgpu_get_info( bspgpu_t * h, bspgpu_info * info );
+int bspgpu_sync( bspgpu_t * h );
+void * bspgpu_host_alloc( size_t bytes );   /* pinned host memory for the host-pointer path */
+void bspgpu_host_free( void * p );
+/* contiguous shard of rank r of `world` over n segments: [first, first+count) */
+void bspgpu_shard_range( uint64_t n, uint32_t rank, uint32_t world, uint64_t * first, uint64_t * count );
+const char * bspgpu_last_error( void );
+uint32_t bspgpu_abi_version( void );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSPGPU_H */

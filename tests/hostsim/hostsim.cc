@@ -1,0 +1,79 @@
+/*
+ * tests/hostsim/hostsim.cc -- TEST-ONLY CPU build of the device trace core.
+ *
+ * Compiles bsp_b200/csrc/trace_core.h (the exact inline functions the sm_100a kernels are
+ * made of) and flatten.cc with g++ -ffp-contract=off, so the flattened image and the
+ * iterative/stack formulation can be checked bit-for-bit against the reference object on
+ * millions of segments in this GPU-less container.  It is not part of libbspgpu.so and the
+ * product never calls it.
+ */
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../bsp_b200/csrc/flatten.h"
+#include "../../bsp_b200/csrc/trace_core.h"
+
+using namespace bspk;
+
+namespace {
+struct Sim {
+	FlatMap flat;
+	ImageMap view;
+	const uint32_t * side_plane;
+};
+std::string g_err;
+}
+
+extern "C" {
+
+void * hostsim_create( const bspgpu_map_desc * lumps ) {
+	Sim * s = new Sim();
+	if( flatten_map( *lumps, s->flat, g_err ) != BSPGPU_OK ) { delete s; return nullptr; }
+	const unsigned char * img = s->flat.image.data();
+	s->view.nodes = ( const NodeRec * ) ( img + s->flat.layout.off_nodes );
+	s->view.refs = ( const BrushRef * ) ( img + s->flat.layout.off_refs );
+	s->view.sides = ( const SideRec * ) ( img + s->flat.layout.off_sides );
+	s->side_plane = ( const uint32_t * ) ( img + s->flat.layout.off_side_plane );
+	return s;
+}
+
+const char * hostsim_error() { return g_err.c_str(); }
+
+void hostsim_destroy( void * h ) { delete ( Sim * ) h; }
+
+void hostsim_layout( void * h, uint64_t * out ) {
+	const MapImageLayout & l = ( ( Sim * ) h )->flat.layout;
+	out[ 0 ] = l.num_nodes; out[ 1 ] = l.num_refs; out[ 2 ] = l.num_sides; out[ 3 ] = l.tree_depth;
+	out[ 4 ] = l.staged_bytes; out[ 5 ] = l.total_bytes;
+}
+
+/* segs: `stride` floats per segment, end point `end_off` floats after the start point */
+void hostsim_trace( void * h, const float * segs, uint64_t stride, uint64_t end_off, uint64_t n, ResultRec * out, float * pos4 ) {
+	const Sim * s = ( const Sim * ) h;
+	for( uint64_t i = 0; i < n; i++ ) {
+		const float * a = segs + i * stride;
+		const float * b = a + end_off;
+		Ray r;
+		r.sx = a[ 0 ]; r.sy = a[ 1 ]; r.sz = a[ 2 ];
+		r.dx = b[ 0 ] - a[ 0 ]; r.dy = b[ 1 ] - a[ 1 ]; r.dz = b[ 2 ] - a[ 2 ];
+		HitState hs;
+		trace_one< ImageMap, 64 >( s->view, r, hs );
+		if( out ) out[ i ] = make_result( hs, s->side_plane );
+		if( pos4 ) {
+			make_pos( r, hs, pos4[ 4 * i + 0 ], pos4[ 4 * i + 1 ], pos4[ 4 * i + 2 ] );
+			pos4[ 4 * i + 3 ] = hs.t;
+		}
+	}
+}
+
+void hostsim_leaf( void * h, const float * pts, uint64_t stride, uint64_t n, int32_t * leaf ) {
+	const Sim * s = ( const Sim * ) h;
+	for( uint64_t i = 0; i < n; i++ ) {
+		const float * p = pts + i * stride;
+		leaf[ i ] = point_leaf( s->view, p[ 0 ], p[ 1 ], p[ 2 ] );
+	}
+}
+
+} // extern "C"
