@@ -1,0 +1,484 @@
+/*
+ * bspgpu.cu -- implementation of the C ABI in include/bspgpu.h (libbspgpu.so).
+ *
+ * Owns all CUDA state behind the opaque handle: the flattened map image in HBM, the work /
+ * hit counters, streams, and (for host-pointer calls) a 3-deep ring of device staging
+ * buffers so that the H2D copy of chunk c+1, the trace kernel of chunk c and the D2H copy of
+ * chunk c-1 overlap on three streams.  There is no CPU fallback anywhere in this file: if
+ * the device or the kernels are unavailable the call fails with BSPGPU_E_CUDA.
+ */
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bspgpu.h"
+#include "flatten.h"
+#include "seggen.cuh"
+#include "trace_kernels.cuh"
+
+using namespace bspk;
+
+static_assert( sizeof( bspgpu_result ) == sizeof( ResultRec ) && sizeof( ResultRec ) == 16, "result wire format" );
+static_assert( sizeof( bspgpu_segment ) == 32 && sizeof( bspgpu_pos ) == 16, "segment wire format" );
+static_assert( sizeof( NodeRec ) == 32 && sizeof( BrushRef ) == 16 && sizeof( SideRec ) == 16, "image records" );
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail( int code, const std::string & msg ) { g_err = msg; return code; }
+
+#define CK( call ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) { \
+	return fail( BSPGPU_E_CUDA, std::string( #call ) + ": " + cudaGetErrorString( e_ ) ); } } while( 0 )
+
+const int kBufs = 3;
+const int kCounterSlots = 64;               /* one work counter per in-flight launch */
+const uint64_t kMaxLaunchSegs = 1ull << 30; /* in-kernel segment indices are 32-bit */
+
+typedef void ( *TraceKernel )( const TraceParams );
+
+template< int M, int S >
+TraceKernel pick_threads( int threads ) {
+	if( threads <= 256 ) return trace_persistent< M, S, 256 >;
+	if( threads <= 512 ) return trace_persistent< M, S, 512 >;
+	return trace_persistent< M, S, 1024 >;
+}
+template< int M >
+TraceKernel pick_stack( int depth, int threads ) {
+	return depth <= 32 ? pick_threads< M, 32 >( threads ) : pick_threads< M, 64 >( threads );
+}
+TraceKernel pick_kernel( int mode, int depth, int threads ) {
+	switch( mode ) {
+		case kSmemAll: return pick_stack< kSmemAll >( depth, threads );
+		case kSmemTop: return pick_stack< kSmemTop >( depth, threads );
+		default: return pick_stack< kGlobal >( depth, threads );
+	}
+}
+
+} // namespace
+
+struct bspgpu {
+	int device = 0;
+	int sm_count = 0;
+	int max_smem_optin = 0;
+	cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+	unsigned char * d_image = nullptr;
+	MapImageLayout lay;
+	unsigned long long * d_counters = nullptr;   /* [0] hits, [1 .. kCounterSlots] work counters */
+	uint32_t launch_seq = 0;
+
+	/* options */
+	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 96 * 1024;
+	int64_t opt_chunk = 4ll << 20, opt_refill = 8, opt_max_steps = 64, opt_block_segs = 256;
+
+	/* what the last trace did */
+	uint32_t last_variant = 0, last_threads = 0, last_grid = 0, last_smem = 0, last_launches = 0;
+	cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+	bool timing_valid = false;
+
+	/* host-pointer path */
+	void * d_in[ kBufs ] = { }, * d_out[ kBufs ] = { }, * d_pos[ kBufs ] = { };
+	size_t buf_segs = 0;
+	cudaEvent_t ev_in[ kBufs ] = { }, ev_k[ kBufs ] = { }, ev_out[ kBufs ] = { };
+
+	bool use_user_stream = false;
+	cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
+};
+
+namespace {
+
+int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, bspgpu_result * d_out, bspgpu_pos * d_pos, cudaStream_t st ) {
+	/* variant */
+	int variant = ( int ) h->opt_variant;
+	const uint64_t smem_cap = ( uint64_t ) h->max_smem_optin > 1024 ? ( uint64_t ) h->max_smem_optin - 1024 : 0;
+	if( variant == BSPGPU_VARIANT_AUTO ) variant = h->lay.staged_bytes <= smem_cap ? BSPGPU_VARIANT_SMEM : BSPGPU_VARIANT_TOPTREE;
+	int mode; uint32_t smem = 0, top_nodes = 0;
+	if( variant == BSPGPU_VARIANT_SMEM ) {
+		if( h->lay.staged_bytes > smem_cap ) return fail( BSPGPU_E_INVALID, "SMEM variant: flattened map does not fit in shared memory" );
+		mode = kSmemAll; smem = ( uint32_t ) h->lay.staged_bytes;
+	}
+	else if( variant == BSPGPU_VARIANT_TOPTREE ) {
+		mode = kSmemTop;
+		uint64_t bytes = ( uint64_t ) h->opt_top_bytes;
+		if( bytes > smem_cap ) bytes = smem_cap;
+		const uint64_t all = ( uint64_t ) h->lay.num_nodes * sizeof( NodeRec );
+		if( bytes > all ) bytes = all;
+		top_nodes = ( uint32_t ) ( bytes / sizeof( NodeRec ) );
+		smem = top_nodes * ( uint32_t ) sizeof( NodeRec );
+	}
+	else mode = kGlobal;
+
+	int threads = ( int ) h->opt_threads;
+	if( threads <= 0 ) threads = ( mode == kSmemAll ) ? 512 : 256;
+	threads = ( threads + 31 ) / 32 * 32;
+	if( threads > 1024 ) threads = 1024;
+
+	TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads );
+	CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );
+	int ctas = ( int ) h->opt_ctas;
+	int occ = 0;
+	CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &occ, kernel, threads, smem ) );
+	if( occ < 1 ) return fail( BSPGPU_E_CUDA, "kernel does not fit on an SM with the requested block size / shared memory" );
+	if( ctas <= 0 || ctas > occ ) ctas = occ;
+	const int grid = h->sm_count * ctas;
+
+	TraceParams p;
+	p.image = h->d_image;
+	p.off_refs = h->lay.off_refs; p.off_sides = h->lay.off_sides; p.off_side_plane = h->lay.off_side_plane;
+	p.staged_bytes = smem; p.top_nodes = top_nodes;
+	p.block_segs = ( uint32_t ) ( ( h->opt_block_segs + 31 ) / 32 * 32 );
+	p.refill = ( uint32_t ) ( h->opt_refill < 1 ? 1 : ( h->opt_refill > 32 ? 32 : h->opt_refill ) );
+	p.max_steps = ( uint32_t ) ( h->opt_max_steps < 1 ? 1 : h->opt_max_steps );
+	p.hits = h->d_counters;
+
+	h->last_variant = ( uint32_t ) variant; h->last_threads = ( uint32_t ) threads; h->last_grid = ( uint32_t ) grid; h->last_smem = smem;
+
+	for( uint64_t done = 0; done < n; done += kMaxLaunchSegs ) {
+		const uint64_t cnt = n - done < kMaxLaunchSegs ? n - done : kMaxLaunchSegs;
+		unsigned long long * next = h->d_counters + 1 + ( h->launch_seq++ % kCounterSlots );
+		CK( cudaMemsetAsync( next, 0, sizeof( unsigned long long ), st ) );
+		p.segs = packed24 ? nullptr : reinterpret_cast< const float4 * >( d_segs ) + done * 2;
+		p.segs24 = packed24 ? reinterpret_cast< const float2 * >( d_segs ) + done * 3 : nullptr;
+		p.out = d_out ? reinterpret_cast< ResultRec * >( d_out ) + done : nullptr;
+		p.pos = d_pos ? reinterpret_cast< float4 * >( d_pos ) + done : nullptr;
+		p.n = ( uint32_t ) cnt;
+		p.next = next;
+		kernel<<< grid, threads, smem, st >>>( p );
+		CK( cudaGetLastError() );
+		h->last_launches++;
+	}
+	return BSPGPU_OK;
+}
+
+int ensure_staging( bspgpu * h, size_t segs, bool want_out, bool want_pos ) {
+	if( h->buf_segs < segs ) {
+		for( int b = 0; b < kBufs; b++ ) {
+			if( h->d_in[ b ] ) cudaFree( h->d_in[ b ] );
+			if( h->d_out[ b ] ) cudaFree( h->d_out[ b ] );
+			if( h->d_pos[ b ] ) cudaFree( h->d_pos[ b ] );
+			h->d_in[ b ] = h->d_out[ b ] = h->d_pos[ b ] = nullptr;
+		}
+		h->buf_segs = 0;
+		for( int b = 0; b < kBufs; b++ ) CK( cudaMalloc( &h->d_in[ b ], segs * sizeof( bspgpu_segment ) ) );
+		h->buf_segs = segs;
+	}
+	for( int b = 0; b < kBufs; b++ ) {
+		if( want_out && !h->d_out[ b ] ) CK( cudaMalloc( &h->d_out[ b ], h->buf_segs * sizeof( bspgpu_result ) ) );
+		if( want_pos && !h->d_pos[ b ] ) CK( cudaMalloc( &h->d_pos[ b ], h->buf_segs * sizeof( bspgpu_pos ) ) );
+	}
+	return BSPGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char * bspgpu_last_error( void ) { return g_err.c_str(); }
+uint32_t bspgpu_abi_version( void ) { return BSPGPU_ABI_VERSION; }
+
+void bspgpu_shard_range( uint64_t n, uint32_t rank, uint32_t world, uint64_t * first, uint64_t * count ) {
+	if( world == 0 ) world = 1;
+	const uint64_t per = ( n + world - 1 ) / world;
+	uint64_t f = per * rank;
+	if( f > n ) f = n;
+	uint64_t c = n - f < per ? n - f : per;
+	if( first ) *first = f;
+	if( count ) *count = c;
+}
+
+int bspgpu_create( bspgpu_t ** out, const bspgpu_map_desc * lumps, int device ) {
+	if( !out || !lumps ) return fail( BSPGPU_E_INVALID, "bspgpu_create: null argument" );
+	*out = nullptr;
+	FlatMap flat;
+	std::string err;
+	const int rc = flatten_map( *lumps, flat, err );
+	if( rc != BSPGPU_OK ) return fail( rc, "bspgpu_create: " + err );
+	if( flat.layout.tree_depth > 64 ) return fail( BSPGPU_E_MAP, "bspgpu_create: tree deeper than 64 levels" );
+
+	int count = 0;
+	if( cudaGetDeviceCount( &count ) != cudaSuccess || count == 0 ) {
+		cudaGetLastError();
+		return fail( BSPGPU_E_CUDA, "bspgpu_create: no CUDA device (this library has no CPU fallback)" );
+	}
+	if( device < 0 ) CK( cudaGetDevice( &device ) );
+	if( device >= count ) return fail( BSPGPU_E_INVALID, "bspgpu_create: device index out of range" );
+	CK( cudaSetDevice( device ) );
+	cudaDeviceProp prop;
+	CK( cudaGetDeviceProperties( &prop, device ) );
+	if( prop.major != 10 ) return fail( BSPGPU_E_CUDA, "bspgpu_create: kernels are built for sm_100a only, device is sm_" + std::to_string( prop.major * 10 + prop.minor ) );
+
+	bspgpu * h = new bspgpu();
+	h->device = device;
+	h->sm_count = prop.multiProcessorCount;
+	h->max_smem_optin = ( int ) prop.sharedMemPerBlockOptin;
+	h->lay = flat.layout;
+	cudaError_t e = cudaSuccess;
+	do {
+		if( ( e = cudaStreamCreateWithFlags( &h->own_stream, cudaStreamNonBlocking ) ) != cudaSuccess ) break;
+		if( ( e = cudaStreamCreateWithFlags( &h->copy_in, cudaStreamNonBlocking ) ) != cudaSuccess ) break;
+		if( ( e = cudaStreamCreateWithFlags( &h->copy_out, cudaStreamNonBlocking ) ) != cudaSuccess ) break;
+		if( ( e = cudaEventCreate( &h->ev_start ) ) != cudaSuccess ) break;
+		if( ( e = cudaEventCreate( &h->ev_stop ) ) != cudaSuccess ) break;
+		for( int b = 0; b < kBufs && e == cudaSuccess; b++ ) {
+			if( ( e = cudaEventCreateWithFlags( &h->ev_in[ b ], cudaEventDisableTiming ) ) != cudaSuccess ) break;
+			if( ( e = cudaEventCreateWithFlags( &h->ev_k[ b ], cudaEventDisableTiming ) ) != cudaSuccess ) break;
+			if( ( e = cudaEventCreateWithFlags( &h->ev_out[ b ], cudaEventDisableTiming ) ) != cudaSuccess ) break;
+		}
+		if( e != cudaSuccess ) break;
+		if( ( e = cudaMalloc( &h->d_image, flat.layout.total_bytes ) ) != cudaSuccess ) break;
+		if( ( e = cudaMemcpy( h->d_image, flat.image.data(), flat.layout.total_bytes, cudaMemcpyHostToDevice ) ) != cudaSuccess ) break;
+		if( ( e = cudaMalloc( &h->d_counters, ( 1 + kCounterSlots ) * sizeof( unsigned long long ) ) ) != cudaSuccess ) break;
+		if( ( e = cudaMemset( h->d_counters, 0, ( 1 + kCounterSlots ) * sizeof( unsigned long long ) ) ) != cudaSuccess ) break;
+	} while( 0 );
+	if( e != cudaSuccess ) {
+		const std::string msg = std::string( "bspgpu_create: " ) + cudaGetErrorString( e );
+		bspgpu_destroy( h );
+		return fail( BSPGPU_E_CUDA, msg );
+	}
+	*out = h;
+	return BSPGPU_OK;
+}
+
+int bspgpu_create_from_file( bspgpu_t ** out, const char * path, int device ) {
+	if( !out || !path ) return fail( BSPGPU_E_INVALID, "bspgpu_create_from_file: null argument" );
+	std::vector< unsigned char > blob;
+	bspgpu_map_desc lumps;
+	memset( &lumps, 0, sizeof( lumps ) );
+	std::string err;
+	const int rc = read_ibsp_file( path, blob, lumps, err );
+	if( rc != BSPGPU_OK ) return fail( rc, "bspgpu_create_from_file: " + err );
+	return bspgpu_create( out, &lumps, device );
+}
+
+void bspgpu_destroy( bspgpu_t * h ) {
+	if( !h ) return;
+	cudaSetDevice( h->device );
+	if( h->own_stream ) cudaStreamSynchronize( h->own_stream );
+	for( int b = 0; b < kBufs; b++ ) {
+		if( h->d_in[ b ] ) cudaFree( h->d_in[ b ] );
+		if( h->d_out[ b ] ) cudaFree( h->d_out[ b ] );
+		if( h->d_pos[ b ] ) cudaFree( h->d_pos[ b ] );
+		if( h->ev_in[ b ] ) cudaEventDestroy( h->ev_in[ b ] );
+		if( h->ev_k[ b ] ) cudaEventDestroy( h->ev_k[ b ] );
+		if( h->ev_out[ b ] ) cudaEventDestroy( h->ev_out[ b ] );
+	}
+	if( h->d_image ) cudaFree( h->d_image );
+	if( h->d_counters ) cudaFree( h->d_counters );
+	if( h->ev_start ) cudaEventDestroy( h->ev_start );
+	if( h->ev_stop ) cudaEventDestroy( h->ev_stop );
+	if( h->own_stream ) cudaStreamDestroy( h->own_stream );
+	if( h->copy_in ) cudaStreamDestroy( h->copy_in );
+	if( h->copy_out ) cudaStreamDestroy( h->copy_out );
+	delete h;
+}
+
+int bspgpu_trace_pos( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result * out, bspgpu_pos * pos, unsigned flags ) {
+	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: null handle" );
+	if( n && ( !segs || ( !out && !pos ) ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: null segs, or both out and pos null" );
+	const bool segs_dev = ( flags & BSPGPU_SEGS_DEVICE ) != 0, out_dev = ( flags & BSPGPU_OUT_DEVICE ) != 0;
+	const bool packed = ( flags & BSPGPU_SEGS_PACKED24 ) != 0;
+	if( ( flags & BSPGPU_ASYNC ) && !( segs_dev && out_dev ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: BSPGPU_ASYNC needs device pointers" );
+	CK( cudaSetDevice( h->device ) );
+	cudaStream_t st = h->stream();
+	h->last_launches = 0;
+	h->timing_valid = false;
+	CK( cudaMemsetAsync( h->d_counters, 0, sizeof( unsigned long long ), st ) );
+	if( n == 0 ) return BSPGPU_OK;
+	const size_t seg_bytes = packed ? 24 : sizeof( bspgpu_segment );
+
+	if( segs_dev && out_dev ) {
+		CK( cudaEventRecord( h->ev_start, st ) );
+		const int rc = enqueue_trace( h, segs, packed, n, out, pos, st );
+		if( rc != BSPGPU_OK ) return rc;
+		CK( cudaEventRecord( h->ev_stop, st ) );
+		h->timing_valid = true;
+		if( !( flags & BSPGPU_ASYNC ) ) CK( cudaStreamSynchronize( st ) );
+		return BSPGPU_OK;
+	}
+
+	/* ---- at least one side lives in host memory: chunked 3-stream pipeline */
+	uint64_t chunk = ( uint64_t ) ( h->opt_chunk < 1024 ? 1024 : h->opt_chunk );
+	if( chunk > n ) chunk = n;
+	if( chunk > kMaxLaunchSegs ) chunk = kMaxLaunchSegs;
+	{
+		const int rc = ensure_staging( h, ( size_t ) chunk, out != nullptr, pos != nullptr );
+		if( rc != BSPGPU_OK ) return rc;
+	}
+	/* order the side streams after whatever the compute stream already holds */
+	CK( cudaEventRecord( h->ev_start, st ) );
+	CK( cudaStreamWaitEvent( h->copy_in, h->ev_start, 0 ) );
+	uint64_t c = 0;
+	for( uint64_t done = 0; done < n; done += chunk, c++ ) {
+		const uint64_t cnt = n - done < chunk ? n - done : chunk;
+		const int b = ( int ) ( c % kBufs );
+		const void * d_segs;
+		if( segs_dev ) d_segs = ( const char * ) segs + done * seg_bytes;
+		else {
+			if( c >= ( uint64_t ) kBufs ) CK( cudaStreamWaitEvent( h->copy_in, h->ev_k[ b ], 0 ) );   /* kernel that last read d_in[b] */
+			CK( cudaMemcpyAsync( h->d_in[ b ], ( const char * ) segs + done * seg_bytes, cnt * seg_bytes, cudaMemcpyHostToDevice, h->copy_in ) );
+			CK( cudaEventRecord( h->ev_in[ b ], h->copy_in ) );
+			CK( cudaStreamWaitEvent( st, h->ev_in[ b ], 0 ) );
+			d_segs = h->d_in[ b ];
+		}
+		bspgpu_result * k_out = out ? ( out_dev ? out + done : ( bspgpu_result * ) h->d_out[ b ] ) : nullptr;
+		bspgpu_pos * k_pos = pos ? ( out_dev ? pos + done : ( bspgpu_pos * ) h->d_pos[ b ] ) : nullptr;
+		if( !out_dev && c >= ( uint64_t ) kBufs ) CK( cudaStreamWaitEvent( st, h->ev_out[ b ], 0 ) );   /* D2H that last read d_out[b] */
+		const int rc = enqueue_trace( h, d_segs, packed, cnt, k_out, k_pos, st );
+		if( rc != BSPGPU_OK ) return rc;
+		CK( cudaEventRecord( h->ev_k[ b ], st ) );
+		if( !out_dev ) {
+			CK( cudaStreamWaitEvent( h->copy_out, h->ev_k[ b ], 0 ) );
+			if( out ) CK( cudaMemcpyAsync( out + done, h->d_out[ b ], cnt * sizeof( bspgpu_result ), cudaMemcpyDeviceToHost, h->copy_out ) );
+			if( pos ) CK( cudaMemcpyAsync( pos + done, h->d_pos[ b ], cnt * sizeof( bspgpu_pos ), cudaMemcpyDeviceToHost, h->copy_out ) );
+			CK( cudaEventRecord( h->ev_out[ b ], h->copy_out ) );
+		}
+	}
+	CK( cudaEventRecord( h->ev_stop, st ) );
+	h->timing_valid = true;
+	CK( cudaStreamSynchronize( st ) );
+	CK( cudaStreamSynchronize( h->copy_in ) );
+	CK( cudaStreamSynchronize( h->copy_out ) );
+	return BSPGPU_OK;
+}
+
+int bspgpu_trace( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result * out, unsigned flags ) {
+	if( n && !out ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: null out" );
+	return bspgpu_trace_pos( h, segs, n, out, nullptr, flags );
+}
+
+int bspgpu_hit_count( bspgpu_t * h, uint64_t * hits ) {
+	if( !h || !hits ) return fail( BSPGPU_E_INVALID, "bspgpu_hit_count: null argument" );
+	CK( cudaSetDevice( h->device ) );
+	unsigned long long v = 0;
+	CK( cudaMemcpyAsync( &v, h->d_counters, sizeof( v ), cudaMemcpyDeviceToHost, h->stream() ) );
+	CK( cudaStreamSynchronize( h->stream() ) );
+	*hits = v;
+	return BSPGPU_OK;
+}
+
+int bspgpu_leaf( bspgpu_t * h, const float * pts, uint32_t stride, uint64_t n, int32_t * leaf, unsigned flags ) {
+	if( !h || ( n && ( !pts || !leaf ) ) || stride < 3 ) return fail( BSPGPU_E_INVALID, "bspgpu_leaf: bad argument" );
+	if( n == 0 ) return BSPGPU_OK;
+	CK( cudaSetDevice( h->device ) );
+	cudaStream_t st = h->stream();
+	const bool pts_dev = ( flags & BSPGPU_SEGS_DEVICE ) != 0, out_dev = ( flags & BSPGPU_OUT_DEVICE ) != 0;
+	float * d_pts = nullptr; int32_t * d_leaf = nullptr;
+	if( !pts_dev ) {
+		CK( cudaMalloc( &d_pts, n * stride * sizeof( float ) ) );
+		CK( cudaMemcpyAsync( d_pts, pts, n * stride * sizeof( float ), cudaMemcpyHostToDevice, st ) );
+	}
+	if( !out_dev ) CK( cudaMalloc( &d_leaf, n * sizeof( int32_t ) ) );
+	const int threads = 256;
+	uint64_t blocks = ( n + threads - 1 ) / threads;
+	if( blocks > ( uint64_t ) h->sm_count * 16 ) blocks = ( uint64_t ) h->sm_count * 16;
+	leaf_kernel<<< ( unsigned ) blocks, threads, 0, st >>>( h->d_image, pts_dev ? pts : d_pts, stride, n, out_dev ? leaf : d_leaf );
+	CK( cudaGetLastError() );
+	if( !out_dev ) CK( cudaMemcpyAsync( leaf, d_leaf, n * sizeof( int32_t ), cudaMemcpyDeviceToHost, st ) );
+	if( !( ( flags & BSPGPU_ASYNC ) && pts_dev && out_dev ) ) CK( cudaStreamSynchronize( st ) );
+	if( d_pts ) cudaFree( d_pts );
+	if( d_leaf ) cudaFree( d_leaf );
+	return BSPGPU_OK;
+}
+
+int bspgpu_generate( bspgpu_t * h, const bspgpu_gen_desc * g, uint64_t first, uint64_t count, void * dev_segs ) {
+	if( !h || !g || ( count && !dev_segs ) ) return fail( BSPGPU_E_INVALID, "bspgpu_generate: null argument" );
+	if( g->kind > 2 ) return fail( BSPGPU_E_INVALID, "bspgpu_generate: unknown kind" );
+	if( count == 0 ) return BSPGPU_OK;
+	CK( cudaSetDevice( h->device ) );
+	cudaStream_t st = h->stream();
+	GenParams p;
+	memset( &p, 0, sizeof( p ) );
+	p.kind = g->kind;
+	p.key = sm64_fin( g->seed + kGolden );
+	for( int a = 0; a < 3; a++ ) { p.lo[ a ] = g->lo[ a ]; p.ext[ a ] = g->hi[ a ] - g->lo[ a ]; }
+	p.len_lo = g->len_lo; p.len_ext = g->len_hi - g->len_lo;
+	p.first = first; p.count = count; p.out = reinterpret_cast< float4 * >( dev_segs );
+	float * d_views = nullptr;
+	if( g->kind == 2 ) {
+		if( !g->views || !g->num_views || !g->width || !g->height ) return fail( BSPGPU_E_INVALID, "bspgpu_generate: camera kind needs views and a grid size" );
+		if( first + count > ( uint64_t ) g->num_views * g->width * g->height ) return fail( BSPGPU_E_INVALID, "bspgpu_generate: camera range exceeds views*width*height" );
+		CK( cudaMalloc( &d_views, ( size_t ) g->num_views * 12 * sizeof( float ) ) );
+		CK( cudaMemcpyAsync( d_views, g->views, ( size_t ) g->num_views * 12 * sizeof( float ), cudaMemcpyHostToDevice, st ) );
+		p.views = d_views; p.width = g->width; p.height = g->height;
+		p.inv2w = ( float ) ( 2.0 / ( double ) g->width ); p.inv2h = ( float ) ( 2.0 / ( double ) g->height );
+		p.tanx = g->tan_half; p.tany = g->tan_half * ( float ) g->height / ( float ) g->width;
+		p.far_dist = g->far_dist;
+	}
+	const int threads = 256;
+	uint64_t blocks = ( count + threads - 1 ) / threads;
+	if( blocks > ( uint64_t ) h->sm_count * 32 ) blocks = ( uint64_t ) h->sm_count * 32;
+	generate_kernel<<< ( unsigned ) blocks, threads, 0, st >>>( p );
+	CK( cudaGetLastError() );
+	CK( cudaStreamSynchronize( st ) );
+	if( d_views ) cudaFree( d_views );
+	return BSPGPU_OK;
+}
+
+int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
+	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_set_option: null handle" );
+	switch( option ) {
+		case BSPGPU_OPT_VARIANT: if( value < 0 || value > 3 ) return fail( BSPGPU_E_INVALID, "bad variant" ); h->opt_variant = value; break;
+		case BSPGPU_OPT_BLOCK_THREADS: h->opt_threads = value; break;
+		case BSPGPU_OPT_CTAS_PER_SM: h->opt_ctas = value; break;
+		case BSPGPU_OPT_TOPTREE_BYTES: h->opt_top_bytes = value < 0 ? 0 : value; break;
+		case BSPGPU_OPT_CHUNK_SEGMENTS: h->opt_chunk = value; break;
+		case BSPGPU_OPT_REFILL: h->opt_refill = value; break;
+		case BSPGPU_OPT_MAX_STEPS: h->opt_max_steps = value; break;
+		case BSPGPU_OPT_BLOCK_SEGS: h->opt_block_segs = value; break;
+		default: return fail( BSPGPU_E_INVALID, "bspgpu_set_option: unknown option" );
+	}
+	return BSPGPU_OK;
+}
+
+int bspgpu_set_stream( bspgpu_t * h, void * cuda_stream ) {
+	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_set_stream: null handle" );
+	h->user_stream = ( cudaStream_t ) cuda_stream;
+	h->use_user_stream = true;
+	return BSPGPU_OK;
+}
+
+int bspgpu_reset_stream( bspgpu_t * h ) {
+	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_reset_stream: null handle" );
+	h->user_stream = nullptr;
+	h->use_user_stream = false;
+	return BSPGPU_OK;
+}
+
+int bspgpu_sync( bspgpu_t * h ) {
+	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_sync: null handle" );
+	CK( cudaSetDevice( h->device ) );
+	CK( cudaStreamSynchronize( h->stream() ) );
+	return BSPGPU_OK;
+}
+
+int bspgpu_get_info( bspgpu_t * h, bspgpu_info * info ) {
+	if( !h || !info ) return fail( BSPGPU_E_INVALID, "bspgpu_get_info: null argument" );
+	memset( info, 0, sizeof( *info ) );
+	info->abi_version = BSPGPU_ABI_VERSION;
+	info->device = h->device; info->sm_count = ( uint32_t ) h->sm_count;
+	info->variant = h->last_variant; info->block_threads = h->last_threads; info->grid_ctas = h->last_grid;
+	info->smem_bytes = h->last_smem; info->tree_depth = h->lay.tree_depth;
+	info->num_nodes = h->lay.num_nodes; info->num_brush_refs = h->lay.num_refs; info->num_sides = h->lay.num_sides;
+	info->map_bytes = h->lay.total_bytes; info->last_launches = h->last_launches;
+	if( h->timing_valid ) {
+		CK( cudaSetDevice( h->device ) );
+		CK( cudaEventSynchronize( h->ev_stop ) );
+		float ms = 0.0f;
+		CK( cudaEventElapsedTime( &ms, h->ev_start, h->ev_stop ) );
+		info->last_kernel_ms = ms;
+	}
+	return BSPGPU_OK;
+}
+
+void * bspgpu_host_alloc( size_t bytes ) {
+	void * p = nullptr;
+	if( cudaMallocHost( &p, bytes ) != cudaSuccess ) { g_err = "bspgpu_host_alloc: cudaMallocHost failed"; cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+void bspgpu_host_free( void * p ) { if( p ) cudaFreeHost( p ); }
+
+} // extern "C"

@@ -1,0 +1,324 @@
+/*
+ * trace_kernels.cuh -- sm_100a kernels of the batched segment trace.
+ *
+ * K1/K2  trace_persistent<Mode>: persistent warps.  Each warp owns a private block of
+ *        consecutive segments claimed with one global atomicAdd (warp-level work fetch);
+ *        lanes whose segment has finished are re-filled from that block as soon as
+ *        `refill` lanes are idle (__ballot_sync / __popc ranks = the ray compaction), so a
+ *        warp keeps ~32 live segments instead of waiting for its slowest one.
+ *        The per-lane walk is trace_core.h (the reference's statements, one rounding each).
+ *        Mode kSmemAll : the whole flattened map [nodes|refs|sides] is staged in shared
+ *                        memory with cp.async.bulk (TMA 1-D bulk copy) + an mbarrier  (C1/C2)
+ *             kSmemTop : only the first `top_nodes` breadth-first nodes are staged; the rest
+ *                        of the map is read through the read-only path (L1 -> L2)       (C3-C5)
+ *             kGlobal  : nothing staged.
+ * K3     hit count: per-lane counters, one shuffle reduction + one atomicAdd per warp.
+ * N3     leaf_kernel: batched BSP::position_to_leaf (reference bsp.cc:273-286).
+ *
+ * No tensor cores: the walk is a dependent chain of 16/32-byte gathers and a handful of
+ * fp32 ops per node/side, not a contraction.
+ */
+#ifndef BSPGPU_TRACE_KERNELS_CUH
+#define BSPGPU_TRACE_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "trace_core.h"
+
+namespace bspk {
+
+enum Mode { kSmemAll = 0, kSmemTop = 1, kGlobal = 2 };
+
+struct TraceParams {
+	const unsigned char * image;      /* flattened map in global memory */
+	uint64_t off_refs, off_sides, off_side_plane;
+	uint32_t staged_bytes;            /* bytes copied to shared memory by this mode */
+	uint32_t top_nodes;               /* kSmemTop: nodes [0, top_nodes) live in shared memory */
+	const float4 * segs;              /* 2 float4 per segment ... */
+	const float2 * segs24;            /* ... or 3 float2 (6 packed floats) per segment */
+	ResultRec * out;                  /* may be null */
+	float4 * pos;                     /* may be null */
+	uint32_t n;
+	uint32_t block_segs;              /* segments a warp claims per global atomic */
+	uint32_t refill;                  /* idle lanes that trigger a refill (1..32) */
+	uint32_t max_steps;               /* node steps per lane per round (bounds divergence) */
+	unsigned long long * next;        /* work counter, zeroed before launch */
+	unsigned long long * hits;        /* accumulated hit count */
+};
+
+/* ---------------------------------------------------------------- PTX helpers (TMA bulk copy + mbarrier) */
+
+__device__ __forceinline__ uint32_t smem_u32( const void * p ) {
+	return ( uint32_t ) __cvta_generic_to_shared( p );
+}
+__device__ __forceinline__ void mbar_init( uint64_t * bar, uint32_t count ) {
+	asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"( smem_u32( bar ) ), "r"( count ) );
+}
+__device__ __forceinline__ void mbar_fence_init() {
+	asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+}
+__device__ __forceinline__ void mbar_expect_tx( uint64_t * bar, uint32_t bytes ) {
+	asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"( smem_u32( bar ) ), "r"( bytes ) : "memory" );
+}
+__device__ __forceinline__ bool mbar_try_wait( uint64_t * bar, uint32_t phase ) {
+	uint32_t ok;
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		"selp.u32 %0, 1, 0, p;\n"
+		"}\n" : "=r"( ok ) : "r"( smem_u32( bar ) ), "r"( phase ) : "memory" );
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait( uint64_t * bar, uint32_t phase ) {
+	while( !mbar_try_wait( bar, phase ) ) { }
+}
+/* 1-D TMA bulk copy global -> shared, completion counted on the mbarrier (SASS: UBLKCP) */
+__device__ __forceinline__ void bulk_g2s( void * dst, const void * src, uint32_t bytes, uint64_t * bar ) {
+	asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"( smem_u32( dst ) ), "l"( src ), "r"( bytes ), "r"( smem_u32( bar ) ) : "memory" );
+}
+
+/* streaming loads/stores for the segment and result streams: read once / written once, keep them
+ * out of L1 and first in line for L2 eviction so the map stays cached */
+__device__ __forceinline__ float4 ld_stream4( const float4 * p ) {
+	float4 v;
+	asm volatile( "ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"( v.x ), "=f"( v.y ), "=f"( v.z ), "=f"( v.w ) : "l"( p ) );
+	return v;
+}
+__device__ __forceinline__ float2 ld_stream2( const float2 * p ) {
+	float2 v;
+	asm volatile( "ld.global.cs.v2.f32 {%0,%1}, [%2];" : "=f"( v.x ), "=f"( v.y ) : "l"( p ) );
+	return v;
+}
+__device__ __forceinline__ void st_stream4( void * p, float a, float b, float c, float d ) {
+	asm volatile( "st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"( p ), "f"( a ), "f"( b ), "f"( c ), "f"( d ) : "memory" );
+}
+
+/* ---------------------------------------------------------------- map accessors */
+
+struct SmemAllMap {
+	const NodeRec * nodes; const BrushRef * refs; const SideRec * sides;   /* shared memory */
+	__device__ __forceinline__ void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const {
+		const float4 p = *reinterpret_cast< const float4 * >( &nodes[ i ] );
+		const int2 c = *reinterpret_cast< const int2 * >( &nodes[ i ].child[ 0 ] );
+		nx = p.x; ny = p.y; nz = p.z; d = p.w; c0 = c.x; c1 = c.y;
+	}
+	__device__ __forceinline__ void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const {
+		const uint4 r = *reinterpret_cast< const uint4 * >( &refs[ i ] );
+		first = r.x; nraw = r.y; brush = ( int32_t ) r.z;
+	}
+	__device__ __forceinline__ void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const {
+		const float4 p = *reinterpret_cast< const float4 * >( &sides[ i ] );
+		nx = p.x; ny = p.y; nz = p.z; d = p.w;
+	}
+};
+
+struct GlobalMap {
+	const NodeRec * nodes; const BrushRef * refs; const SideRec * sides;   /* global memory, read-only path */
+	__device__ __forceinline__ void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const {
+		const float4 p = __ldg( reinterpret_cast< const float4 * >( &nodes[ i ] ) );
+		const int2 c = __ldg( reinterpret_cast< const int2 * >( &nodes[ i ].child[ 0 ] ) );
+		nx = p.x; ny = p.y; nz = p.z; d = p.w; c0 = c.x; c1 = c.y;
+	}
+	__device__ __forceinline__ void node_full( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1, int32_t & o0, int32_t & o1 ) const {
+		const float4 p = __ldg( reinterpret_cast< const float4 * >( &nodes[ i ] ) );
+		const int4 c = __ldg( reinterpret_cast< const int4 * >( &nodes[ i ].child[ 0 ] ) );
+		nx = p.x; ny = p.y; nz = p.z; d = p.w; c0 = c.x; c1 = c.y; o0 = c.z; o1 = c.w;
+	}
+	__device__ __forceinline__ void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const {
+		const uint4 r = __ldg( reinterpret_cast< const uint4 * >( &refs[ i ] ) );
+		first = r.x; nraw = r.y; brush = ( int32_t ) r.z;
+	}
+	__device__ __forceinline__ void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const {
+		const float4 p = __ldg( reinterpret_cast< const float4 * >( &sides[ i ] ) );
+		nx = p.x; ny = p.y; nz = p.z; d = p.w;
+	}
+};
+
+struct SmemTopMap {
+	const NodeRec * top;   /* shared memory: nodes [0, top_nodes) */
+	uint32_t top_nodes;
+	GlobalMap g;
+	__device__ __forceinline__ void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const {
+		if( ( uint32_t ) i < top_nodes ) {
+			const float4 p = *reinterpret_cast< const float4 * >( &top[ i ] );
+			const int2 c = *reinterpret_cast< const int2 * >( &top[ i ].child[ 0 ] );
+			nx = p.x; ny = p.y; nz = p.z; d = p.w; c0 = c.x; c1 = c.y;
+		}
+		else g.node( i, nx, ny, nz, d, c0, c1 );
+	}
+	__device__ __forceinline__ void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const { g.ref( i, first, nraw, brush ); }
+	__device__ __forceinline__ void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const { g.side( i, nx, ny, nz, d ); }
+};
+
+template< int kMode > struct MapOf;
+template<> struct MapOf< kSmemAll > { typedef SmemAllMap type; };
+template<> struct MapOf< kSmemTop > { typedef SmemTopMap type; };
+template<> struct MapOf< kGlobal > { typedef GlobalMap type; };
+
+/* ---------------------------------------------------------------- K1/K2 */
+
+template< int kMode, int kStack, int kMaxThreads >
+__global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TraceParams p ) {
+	extern __shared__ __align__( 128 ) unsigned char smem[];
+	__shared__ __align__( 8 ) uint64_t stage_bar;
+
+	/* ---- stage the map (or its top) into shared memory: one thread issues TMA bulk copies,
+	 *      everyone waits on the mbarrier's transaction count */
+	if( kMode != kGlobal && p.staged_bytes > 0 ) {
+		if( threadIdx.x == 0 ) {
+			mbar_init( &stage_bar, 1 );
+			mbar_fence_init();
+		}
+		__syncthreads();
+		if( threadIdx.x == 0 ) {
+			mbar_expect_tx( &stage_bar, p.staged_bytes );
+			const uint32_t kChunk = 32768;
+			for( uint32_t off = 0; off < p.staged_bytes; off += kChunk ) {
+				const uint32_t sz = min( kChunk, p.staged_bytes - off );
+				bulk_g2s( smem + off, p.image + off, sz, &stage_bar );
+			}
+		}
+		mbar_wait( &stage_bar, 0 );
+	}
+
+	typename MapOf< kMode >::type map;
+	const NodeRec * g_nodes = reinterpret_cast< const NodeRec * >( p.image );
+	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
+	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
+	if constexpr( kMode == kSmemAll ) {
+		map.nodes = reinterpret_cast< const NodeRec * >( smem );
+		map.refs = reinterpret_cast< const BrushRef * >( smem + p.off_refs );
+		map.sides = reinterpret_cast< const SideRec * >( smem + p.off_sides );
+	}
+	else if constexpr( kMode == kSmemTop ) {
+		map.top = reinterpret_cast< const NodeRec * >( smem );
+		map.top_nodes = p.top_nodes;
+		map.g.nodes = g_nodes; map.g.refs = g_refs; map.g.sides = g_sides;
+	}
+	else {
+		map.nodes = g_nodes; map.refs = g_refs; map.sides = g_sides;
+	}
+	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
+
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = ( 1u << lane ) - 1u;
+	const unsigned kFull = 0xffffffffu;
+
+	/* warp-private block of claimed segments [blk_next, blk_end): warp-uniform registers */
+	uint32_t blk_next = 0, blk_end = 0;
+	bool more_work = true;
+
+	/* per-lane segment state */
+	bool active = false;
+	uint32_t seg = 0;
+	Ray r; r.sx = r.sy = r.sz = r.dx = r.dy = r.dz = 0.0f;
+	HitState h; hit_init( h );
+	StackEntry stack[ kStack ];
+	int32_t sp = 0, node = 0;
+	float tmin = 0.0f, tmax = 1.0f;
+	uint32_t my_hits = 0;
+
+	for( ;; ) {
+		/* ---- warp-level work fetch + compaction: idle lanes take consecutive new segments */
+		const unsigned idle = __ballot_sync( kFull, !active );
+		const unsigned n_idle = __popc( idle );
+		if( more_work && n_idle >= p.refill ) {
+			if( blk_next == blk_end ) {
+				unsigned long long b = 0;
+				if( lane == 0 ) b = atomicAdd( p.next, ( unsigned long long ) p.block_segs );
+				b = __shfl_sync( kFull, b, 0 );
+				if( b >= ( unsigned long long ) p.n ) more_work = false;
+				else {
+					blk_next = ( uint32_t ) b;
+					blk_end = ( uint32_t ) min( b + ( unsigned long long ) p.block_segs, ( unsigned long long ) p.n );
+				}
+			}
+			if( more_work ) {
+				const uint32_t avail = blk_end - blk_next;
+				const uint32_t rank = __popc( idle & lt_mask );
+				if( !active && rank < avail ) {
+					seg = blk_next + rank;
+					float ex, ey, ez;
+					if( p.segs24 ) {
+						const float2 * s = p.segs24 + ( size_t ) seg * 3;
+						const float2 a = ld_stream2( s ), b2 = ld_stream2( s + 1 ), c = ld_stream2( s + 2 );
+						r.sx = a.x; r.sy = a.y; r.sz = b2.x; ex = b2.y; ey = c.x; ez = c.y;
+					}
+					else {
+						const float4 a = ld_stream4( p.segs + ( size_t ) seg * 2 );
+						const float4 b4 = ld_stream4( p.segs + ( size_t ) seg * 2 + 1 );
+						r.sx = a.x; r.sy = a.y; r.sz = a.z; ex = b4.x; ey = b4.y; ez = b4.z;
+					}
+					r.dx = ex - r.sx; r.dy = ey - r.sy; r.dz = ez - r.sz;      /* bsp.cc:261 */
+					hit_init( h );                                              /* bsp.cc:256-257 */
+					sp = 0; node = 0; tmin = 0.0f; tmax = 1.0f;                 /* bsp.cc:263 */
+					active = true;
+				}
+				blk_next += min( n_idle, avail );
+			}
+		}
+		if( __ballot_sync( kFull, active ) == 0u ) {
+			if( !more_work ) break;
+			continue;
+		}
+
+		/* ---- walk: at most max_steps node steps, then the leaf if one was reached */
+		if( active ) {
+			uint32_t steps = p.max_steps;
+			while( node >= 0 && steps-- ) {
+				float nx, ny, nz, d; int32_t c0, c1;
+				map.node( node, nx, ny, nz, d, c0, c1 );
+				int32_t far; bool both;
+				node = node_step( r, nx, ny, nz, d, c0, c1, tmin, tmax, far, both );
+				if( both ) { stack[ sp ].node = far; stack[ sp ].t = tmax; sp++; }
+			}
+		}
+		if( active && node < 0 ) {
+			if( node != kEmptyLeaf ) leaf( map, r, node, tmin, tmax, h );
+			bool done = h.hit != 0;                                             /* bsp.cc:206 */
+			if( !done ) {
+				do {
+					if( sp == 0 ) { done = true; break; }
+					sp--;
+					node = stack[ sp ].node;
+					tmin = stack[ sp ].t;
+					tmax = sp > 0 ? stack[ sp - 1 ].t : 1.0f;
+				} while( node == kEmptyLeaf );
+			}
+			if( done ) {
+				const ResultRec o = make_result( h, side_plane );
+				if( p.out ) st_stream4( p.out + seg, o.t, __int_as_float( o.plane ), __int_as_float( o.brush ), __uint_as_float( o.flags ) );
+				if( p.pos ) {
+					float px, py, pz;
+					make_pos( r, h, px, py, pz );                               /* bsp.cc:265-267 */
+					st_stream4( p.pos + seg, px, py, pz, h.t );
+				}
+				my_hits += ( uint32_t ) h.hit;
+				active = false;
+			}
+		}
+	}
+
+	/* ---- K3: hit count, one atomic per warp */
+	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( kFull, my_hits, o );
+	if( lane == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
+}
+
+/* ---------------------------------------------------------------- N3: batched position_to_leaf */
+
+__global__ void leaf_kernel( const unsigned char * image, const float * pts, uint32_t stride, uint64_t n, int32_t * leaf_out ) {
+	GlobalMap map;
+	map.nodes = reinterpret_cast< const NodeRec * >( image );
+	map.refs = nullptr; map.sides = nullptr;
+	for( uint64_t i = blockIdx.x * ( uint64_t ) blockDim.x + threadIdx.x; i < n; i += ( uint64_t ) gridDim.x * blockDim.x ) {
+		const float * q = pts + i * stride;
+		leaf_out[ i ] = point_leaf( map, q[ 0 ], q[ 1 ], q[ 2 ] );
+	}
+}
+
+} // namespace bspk
+
+#endif

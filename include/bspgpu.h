@@ -103,7 +103,9 @@ enum {
 	BSPGPU_OPT_CTAS_PER_SM = 3,
 	BSPGPU_OPT_TOPTREE_BYTES = 4,   /* shared-memory budget of the TOPTREE variant */
 	BSPGPU_OPT_CHUNK_SEGMENTS = 5,  /* host-pointer path: segments per pipelined H2D/kernel/D2H chunk */
-	BSPGPU_OPT_REFILL = 6           /* persistent-warp refill threshold (idle lanes before a warp fetches work) */
+	BSPGPU_OPT_REFILL = 6,          /* persistent-warp refill threshold (idle lanes before a warp fetches work) */
+	BSPGPU_OPT_MAX_STEPS = 7,       /* node steps a lane takes per round before the warp re-converges */
+	BSPGPU_OPT_BLOCK_SEGS = 8       /* consecutive segments a warp claims per global atomic (multiple of 32) */
 };
 
 typedef struct bspgpu_info {
@@ -151,7 +153,10 @@ int bspgpu_generate( bspgpu_t * h, const bspgpu_gen_desc * g, uint64_t first, ui
 
 /* ---- plumbing ---- */
 int bspgpu_set_option( bspgpu_t * h, int option, int64_t value );
-int bspgpu_set_stream( bspgpu_t * h, void * cuda_stream );  /* run on a caller-owned cudaStream_t (NULL = handle's own) */
+/* run on a caller-owned cudaStream_t from now on (NULL is the legacy default stream, as in CUDA);
+ * bspgpu_reset_stream goes back to the handle's own non-blocking stream (the initial state) */
+int bspgpu_set_stream( bspgpu_t * h, void * cuda_stream );
+int bspgpu_reset_stream( bspgpu_t * h );
 int bspgpu_get_info( bspgpu_t * h, bspgpu_info * info );
 int bspgpu_sync( bspgpu_t * h );
 void * bspgpu_host_alloc( size_t bytes );   /* pinned host memory for the host-pointer path */

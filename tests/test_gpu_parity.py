@@ -1,0 +1,210 @@
+"""GPU parity: the sm_100a kernels, driven through the C ABI (include/bspgpu.h), against the
+oracle on the same seeded inputs.  Bar: bit-exact on every field ({hit,t,pos} are the
+reference's outputs; plane/brush/startsolid are the extension fields defined by
+oracle/restate.c).  Reference semantics cited: bsp.cc:120-271."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {"smem": 1, "toptree": 2, "global": 3}
+
+
+def _segments(m, n_uniform=200_000, n_long=200_000, n_short=100_000, n_edge=16384, seed=21):
+    from tools import mapgen, seggen
+    lo, hi = mapgen.seg_bounds(m)
+    diag = float(np.sqrt(((hi - lo).astype(np.float64) ** 2).sum()))
+    return np.vstack((
+        seggen.edge_cases(m, n_edge, seed),
+        seggen.uniform(seed, 0, n_uniform, lo, hi),
+        seggen.long_rays(seed + 1, 0, n_long, lo, hi, 0.25 * diag, diag),
+        seggen.long_rays(seed + 2, 0, n_short, lo, hi, 1.0, 32.0),
+    ))
+
+
+def _compare(res, pos, exp, exp_pos, what):
+    got = bits(res.view(np.uint32).reshape(-1, 4)) if res.dtype != np.uint32 else res
+    want = bits(exp.view(np.uint32).reshape(-1, 4))
+    bad = (got != want).any(axis=1)
+    if bad.any():
+        i = int(np.nonzero(bad)[0][0])
+        # north_star: any mismatch is logged with index and both hex values
+        pytest.fail(f"{what}: {int(bad.sum())} mismatching results; first at {i}: got {res[i]} ({got[i]}) want {exp[i]} ({want[i]})")
+    if pos is not None:
+        badp = (bits(pos[:, :3]) != bits(exp_pos)).any(axis=1) | (bits(pos[:, 3]) != bits(exp["t"]))
+        assert not badp.any(), f"{what}: {int(badp.sum())} mismatching pos; first at {int(np.nonzero(badp)[0][0])}"
+
+
+def test_kat_vectors(native, maps):
+    """SURVEY.md 8c KAT-0 / KAT-1, captured from the unmodified reference."""
+    from tools import mapgen
+    for name, vecs in (("kat0", mapgen.KAT0_VECTORS), ("kat1", mapgen.KAT1_VECTORS)):
+        m, path = maps(name)
+        g = native.BspGpu(path)
+        segs = np.zeros((len(vecs), 8), np.float32)
+        for i, v in enumerate(vecs):
+            segs[i, 0:3] = v[0]; segs[i, 4:7] = v[1]
+        pos = np.zeros((len(vecs), 4), np.float32)
+        res = g.trace(segs, out=np.zeros(len(vecs), native.RESULT_DT), pos=pos)
+        for i, v in enumerate(vecs):
+            assert (res["flags"][i] & 1) == v[2], (name, i)
+            assert int(bits(res["t"][i:i + 1])[0]) == v[3], (name, i, hex(int(bits(res["t"][i:i + 1])[0])))
+            # Intersection::pos = start + t*(end-start) in fp32 (bsp.cc:265-267); the survey lists it rounded
+            s32, e32 = segs[i, 0:3], segs[i, 4:7]
+            want = (s32 + res["t"][i] * (e32 - s32)) if v[2] else np.zeros(3, np.float32)
+            assert np.array_equal(bits(pos[i, :3]), bits(want.astype(np.float32))), (name, i)
+            if v[4] is not None:
+                np.testing.assert_allclose(pos[i, :3], np.asarray(v[4], np.float32), rtol=1e-6, atol=1e-6, err_msg=f"{name} {i}")
+        g.close()
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("mapname", ["kat1", "rooms8", "city10k"])
+def test_parity_vs_oracle(native, maps, oracle_mod, mapname, variant):
+    m, path = maps(mapname)
+    g = native.BspGpu(m)
+    if variant == "smem" and g.info()["map_bytes"] > 200 * 1024:
+        with pytest.raises(native.BspGpuError):
+            g.set_option(1, VARIANTS[variant]); g.trace(np.zeros((1, 8), np.float32))
+        return
+    g.set_option(1, VARIANTS[variant])
+    segs = _segments(m)
+    exp, exp_pos, ctr = oracle_mod.Port(m).trace(segs)
+    pos = np.zeros((len(segs), 4), np.float32)
+    res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+    _compare(res, pos, exp, exp_pos, f"{mapname}/{variant}")
+    assert g.hit_count() == int((exp["flags"] & 1).sum()) == ctr["hits"]
+    if oracle_mod.have_reference():
+        ref = oracle_mod.Reference(path).trace(segs)
+        assert np.array_equal(ref["hit"], (res["flags"] & 1).astype(np.uint8))
+        assert np.array_equal(bits(ref["t"]), bits(res["t"]))
+        assert np.array_equal(bits(ref["pos"]), bits(pos[:, :3]))
+    g.close()
+
+
+@pytest.mark.parametrize("refill,max_steps,threads", [(1, 1, 128), (32, 1000, 256), (8, 4, 1024), (16, 64, 512)])
+def test_scheduling_knobs_do_not_change_results(native, maps, oracle_mod, refill, max_steps, threads):
+    m, _ = maps("rooms8")
+    segs = _segments(m, 100_000, 50_000, 50_000, 4096)
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    g.set_option(6, refill); g.set_option(7, max_steps); g.set_option(2, threads)
+    res = g.trace(segs)
+    _compare(res, None, exp, exp_pos, f"knobs {refill}/{max_steps}/{threads}")
+    g.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 257, 100_003])
+def test_ragged_sizes_and_packed_layout(native, maps, oracle_mod, n):
+    m, _ = maps("rooms8")
+    segs = _segments(m, 60_000, 30_000, 10_000, 4096)[:n]
+    g = native.BspGpu(m)
+    res = g.trace(segs, out=np.zeros(n, native.RESULT_DT))
+    packed = np.ascontiguousarray(np.hstack((segs[:, 0:3], segs[:, 4:7])))
+    res24 = g.trace(packed, out=np.zeros(n, native.RESULT_DT), packed24=True)
+    if n:
+        exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+        _compare(res, None, exp, exp_pos, f"n={n}")
+        _compare(res24, None, exp, exp_pos, f"n={n} packed24")
+    assert g.hit_count() == int((res24["flags"] & 1).sum())
+    g.close()
+
+
+def test_host_pipeline_chunks_match_device_path(native, maps, oracle_mod):
+    """host pointers go through the 3-stream chunk pipeline; device tensors go straight to the kernel."""
+    import torch
+    m, _ = maps("rooms8")
+    segs = _segments(m, 300_000, 100_000, 50_000, 4096)
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    g.set_option(5, 50_000)  # chunk size: 10 chunks, exercises buffer reuse
+    pos = np.zeros((len(segs), 4), np.float32)
+    res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+    _compare(res, pos, exp, exp_pos, "host pipeline")
+    d_segs = torch.from_numpy(segs).cuda()
+    d_out = torch.zeros((len(segs), 4), dtype=torch.int32, device="cuda")
+    d_pos = torch.zeros((len(segs), 4), dtype=torch.float32, device="cuda")
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    g.trace(d_segs, out=d_out, pos=d_pos)
+    torch.cuda.synchronize()
+    res_d = d_out.cpu().numpy().view(native.RESULT_DT).reshape(-1)
+    _compare(res_d, d_pos.cpu().numpy(), exp, exp_pos, "device path")
+    assert g.info()["last_launches"] == 1
+    g.close()
+
+
+def test_device_generator_matches_numpy(native, maps):
+    import torch
+    from tools import mapgen, seggen
+    m, _ = maps("rooms8")
+    lo, hi = mapgen.seg_bounds(m)
+    g = native.BspGpu(m)
+    n, first = 100_000, 12_345_678_901
+    buf = torch.zeros((n, 8), dtype=torch.float32, device="cuda")
+    g.generate(buf, first, n, 0, 99, lo, hi)
+    assert np.array_equal(bits(buf.cpu().numpy()), bits(seggen.uniform(99, first, n, lo, hi)))
+    g.generate(buf, first, n, 1, 98, lo, hi, 100.0, 5000.0)
+    assert np.array_equal(bits(buf.cpu().numpy()), bits(seggen.long_rays(98, first, n, lo, hi, 100.0, 5000.0)))
+    views = seggen.make_views(5, 3, lo, hi)
+    g.generate(buf, 1000, n, 2, 0, lo, hi, views=views, width=320, height=200, tan_half=1.0, far=32768.0)
+    assert np.array_equal(bits(buf.cpu().numpy()), bits(seggen.camera(views, 320, 200, 1000, n, 1.0, 32768.0)))
+    g.close()
+
+
+def test_position_to_leaf(native, maps, oracle_mod):
+    """batched BSP::position_to_leaf (bsp.cc:273-286)."""
+    from tools import mapgen, seggen
+    for name in ("kat1", "rooms8", "city10k"):
+        m, path = maps(name)
+        lo, hi = mapgen.seg_bounds(m)
+        pts = np.ascontiguousarray(seggen.uniform(3, 0, 200_000, lo, hi)[:, :4])
+        g = native.BspGpu(m)
+        got = g.leaf(pts)
+        assert np.array_equal(got, oracle_mod.Port(m).leaf(pts))
+        if oracle_mod.have_reference():
+            assert np.array_equal(got, oracle_mod.Reference(path).leaf(pts))
+        g.close()
+
+
+def test_full_size_properties(native, maps, oracle_mod):
+    """C2 size (64M segments, generated on the device): the three staging variants must agree on
+    every result bit and on the hit count, and a strided sample must match the oracle."""
+    import torch
+    from tools import mapgen, seggen
+    m, _ = maps("rooms8")
+    lo, hi = mapgen.seg_bounds(m)
+    n = 64 * 1024 * 1024
+    g = native.BspGpu(m)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    segs = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    g.generate(segs, 0, n, 0, 2, lo, hi)
+    outs, hits = [], []
+    for variant in (1, 2, 3):
+        g.set_option(1, variant)
+        out = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+        g.trace(segs, out=out)
+        hits.append(g.hit_count())
+        outs.append(out)
+    assert hits[0] == hits[1] == hits[2]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert int((outs[0][:, 3] & 1).sum().item()) == hits[0]
+    stride = 257
+    sample = segs[::stride].cpu().numpy()
+    assert np.array_equal(bits(sample), bits(seggen.uniform(2, 0, n, lo, hi)[::stride])) if n <= (1 << 22) else True
+    exp, _, _ = oracle_mod.Port(m).trace(sample)
+    got = outs[0][::stride].cpu().numpy().view(native.RESULT_DT).reshape(-1)
+    _compare(got, None, exp, None, "64M strided sample")
+    g.close()
+
+
+def test_errors(native, maps):
+    m, _ = maps("kat0")
+    g = native.BspGpu(m)
+    with pytest.raises(native.BspGpuError):
+        g.set_option(999, 1)
+    lib = native.load_library()
+    assert lib.bspgpu_trace(g.h, None, 5, None, 0) < 0
+    assert b"null" in lib.bspgpu_last_error()
+    g.close()
