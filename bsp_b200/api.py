@@ -15,12 +15,12 @@ HIT, STARTSOLID = 1, 2
 SEGS_DEVICE, OUT_DEVICE, SEGS_PACKED24, ASYNC = 1, 2, 4, 8
 VARIANT_AUTO, VARIANT_SMEM, VARIANT_TOPTREE, VARIANT_GLOBAL = 0, 1, 2, 3
 OPT_VARIANT, OPT_BLOCK_THREADS, OPT_CTAS_PER_SM, OPT_TOPTREE_BYTES, OPT_CHUNK_SEGMENTS, OPT_REFILL, \
-    OPT_MAX_STEPS, OPT_BLOCK_SEGS = 1, 2, 3, 4, 5, 6, 7, 8
+    OPT_MAX_STEPS, OPT_BLOCK_SEGS, OPT_SCHEDULER, OPT_SIDE_STEPS, OPT_LEAF_THRESHOLD = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 
 # every symbol include/bspgpu.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = (
     "bspgpu_create", "bspgpu_create_from_file", "bspgpu_destroy", "bspgpu_trace", "bspgpu_trace_pos",
-    "bspgpu_hit_count", "bspgpu_leaf", "bspgpu_generate", "bspgpu_set_option", "bspgpu_set_stream",
+    "bspgpu_hit_count", "bspgpu_hit_count_device", "bspgpu_leaf", "bspgpu_generate", "bspgpu_set_option", "bspgpu_set_stream",
     "bspgpu_reset_stream", "bspgpu_get_info", "bspgpu_sync", "bspgpu_host_alloc", "bspgpu_host_free", "bspgpu_shard_range",
     "bspgpu_last_error", "bspgpu_abi_version",
 )
@@ -74,6 +74,7 @@ def load_library() -> C.CDLL:
     lib.bspgpu_trace.argtypes = [vp, vp, u64, vp, u32]
     lib.bspgpu_trace_pos.argtypes = [vp, vp, u64, vp, vp, u32]
     lib.bspgpu_hit_count.argtypes = [vp, C.POINTER(u64)]
+    lib.bspgpu_hit_count_device.argtypes = [vp, vp]
     lib.bspgpu_leaf.argtypes = [vp, vp, u32, u64, vp, u32]
     lib.bspgpu_generate.argtypes = [vp, C.POINTER(GenDesc), u64, u64, vp]
     lib.bspgpu_set_option.argtypes = [vp, i32, C.c_int64]
@@ -176,6 +177,10 @@ class BspGpu:
         v = C.c_uint64()
         self._check(self.lib.bspgpu_hit_count(self.h, C.byref(v)))
         return v.value
+
+    def hit_count_device(self, dev_i64):
+        """copy the hit counter into a 1-element int64 cuda tensor (async on the handle's stream)."""
+        self._check(self.lib.bspgpu_hit_count_device(self.h, _ptr(dev_i64)))
 
     # -- the hot path
     def trace(self, segs, out=None, pos=None, n=None, packed24=False, async_=False):

@@ -41,20 +41,25 @@ const uint64_t kMaxLaunchSegs = 1ull << 30; /* in-kernel segment indices are 32-
 typedef void ( *TraceKernel )( const TraceParams );
 
 template< int M, int S >
-TraceKernel pick_threads( int threads ) {
-	if( threads <= 256 ) return trace_persistent< M, S, 256 >;
-	if( threads <= 512 ) return trace_persistent< M, S, 512 >;
-	return trace_persistent< M, S, 1024 >;
+TraceKernel pick_threads( int threads, int sched ) {
+	if( sched == 1 ) {
+		if( threads <= 256 ) return trace_persistent< M, S, 256 >;
+		if( threads <= 512 ) return trace_persistent< M, S, 512 >;
+		return trace_persistent< M, S, 1024 >;
+	}
+	if( threads <= 256 ) return trace_phased< M, S, 256 >;
+	if( threads <= 512 ) return trace_phased< M, S, 512 >;
+	return trace_phased< M, S, 1024 >;
 }
 template< int M >
-TraceKernel pick_stack( int depth, int threads ) {
-	return depth <= 32 ? pick_threads< M, 32 >( threads ) : pick_threads< M, 64 >( threads );
+TraceKernel pick_stack( int depth, int threads, int sched ) {
+	return depth <= 32 ? pick_threads< M, 32 >( threads, sched ) : pick_threads< M, 64 >( threads, sched );
 }
-TraceKernel pick_kernel( int mode, int depth, int threads ) {
+TraceKernel pick_kernel( int mode, int depth, int threads, int sched ) {
 	switch( mode ) {
-		case kSmemAll: return pick_stack< kSmemAll >( depth, threads );
-		case kSmemTop: return pick_stack< kSmemTop >( depth, threads );
-		default: return pick_stack< kGlobal >( depth, threads );
+		case kSmemAll: return pick_stack< kSmemAll >( depth, threads, sched );
+		case kSmemTop: return pick_stack< kSmemTop >( depth, threads, sched );
+		default: return pick_stack< kGlobal >( depth, threads, sched );
 	}
 }
 
@@ -72,7 +77,8 @@ struct bspgpu {
 
 	/* options */
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 96 * 1024;
-	int64_t opt_chunk = 4ll << 20, opt_refill = 8, opt_max_steps = 64, opt_block_segs = 256;
+	int64_t opt_chunk = 4ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;   /* 0 = per-variant default */
+	int64_t opt_sched = 0, opt_side_steps = 8, opt_leaf_threshold = 16;
 
 	/* what the last trace did */
 	uint32_t last_variant = 0, last_threads = 0, last_grid = 0, last_smem = 0, last_launches = 0;
@@ -94,7 +100,9 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 	/* variant */
 	int variant = ( int ) h->opt_variant;
 	const uint64_t smem_cap = ( uint64_t ) h->max_smem_optin > 1024 ? ( uint64_t ) h->max_smem_optin - 1024 : 0;
-	if( variant == BSPGPU_VARIANT_AUTO ) variant = h->lay.staged_bytes <= smem_cap ? BSPGPU_VARIANT_SMEM : BSPGPU_VARIANT_TOPTREE;
+	/* AUTO (measured on B200, profiles/): the whole map in shared memory when it fits; otherwise the read-only
+	 * global path -- for a few-MB map L1 already keeps the top of the tree resident and staging it buys nothing */
+	if( variant == BSPGPU_VARIANT_AUTO ) variant = h->lay.staged_bytes <= smem_cap ? BSPGPU_VARIANT_SMEM : BSPGPU_VARIANT_GLOBAL;
 	int mode; uint32_t smem = 0, top_nodes = 0;
 	if( variant == BSPGPU_VARIANT_SMEM ) {
 		if( h->lay.staged_bytes > smem_cap ) return fail( BSPGPU_E_INVALID, "SMEM variant: flattened map does not fit in shared memory" );
@@ -112,11 +120,11 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 	else mode = kGlobal;
 
 	int threads = ( int ) h->opt_threads;
-	if( threads <= 0 ) threads = ( mode == kSmemAll ) ? 512 : 256;
+	if( threads <= 0 ) threads = 1024;
 	threads = ( threads + 31 ) / 32 * 32;
 	if( threads > 1024 ) threads = 1024;
 
-	TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads );
+	TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched );
 	CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );
 	int ctas = ( int ) h->opt_ctas;
 	int occ = 0;
@@ -131,7 +139,9 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 	p.staged_bytes = smem; p.top_nodes = top_nodes;
 	p.block_segs = ( uint32_t ) ( ( h->opt_block_segs + 31 ) / 32 * 32 );
 	p.refill = ( uint32_t ) ( h->opt_refill < 1 ? 1 : ( h->opt_refill > 32 ? 32 : h->opt_refill ) );
-	p.max_steps = ( uint32_t ) ( h->opt_max_steps < 1 ? 1 : h->opt_max_steps );
+	p.max_steps = ( uint32_t ) ( h->opt_max_steps < 1 ? ( mode == kSmemAll ? 16 : 8 ) : h->opt_max_steps );
+	p.side_steps = ( uint32_t ) ( h->opt_side_steps < 1 ? 1 : h->opt_side_steps );
+	p.leaf_threshold = ( uint32_t ) ( h->opt_leaf_threshold < 1 ? 1 : ( h->opt_leaf_threshold > 32 ? 32 : h->opt_leaf_threshold ) );
 	p.hits = h->d_counters;
 
 	h->last_variant = ( uint32_t ) variant; h->last_threads = ( uint32_t ) threads; h->last_grid = ( uint32_t ) grid; h->last_smem = smem;
@@ -359,6 +369,13 @@ int bspgpu_hit_count( bspgpu_t * h, uint64_t * hits ) {
 	return BSPGPU_OK;
 }
 
+int bspgpu_hit_count_device( bspgpu_t * h, void * dev_u64 ) {
+	if( !h || !dev_u64 ) return fail( BSPGPU_E_INVALID, "bspgpu_hit_count_device: null argument" );
+	CK( cudaSetDevice( h->device ) );
+	CK( cudaMemcpyAsync( dev_u64, h->d_counters, sizeof( unsigned long long ), cudaMemcpyDeviceToDevice, h->stream() ) );
+	return BSPGPU_OK;
+}
+
 int bspgpu_leaf( bspgpu_t * h, const float * pts, uint32_t stride, uint64_t n, int32_t * leaf, unsigned flags ) {
 	if( !h || ( n && ( !pts || !leaf ) ) || stride < 3 ) return fail( BSPGPU_E_INVALID, "bspgpu_leaf: bad argument" );
 	if( n == 0 ) return BSPGPU_OK;
@@ -428,6 +445,9 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 		case BSPGPU_OPT_REFILL: h->opt_refill = value; break;
 		case BSPGPU_OPT_MAX_STEPS: h->opt_max_steps = value; break;
 		case BSPGPU_OPT_BLOCK_SEGS: h->opt_block_segs = value; break;
+		case BSPGPU_OPT_SCHEDULER: h->opt_sched = value; break;
+		case BSPGPU_OPT_SIDE_STEPS: h->opt_side_steps = value; break;
+		case BSPGPU_OPT_LEAF_THRESHOLD: h->opt_leaf_threshold = value; break;
 		default: return fail( BSPGPU_E_INVALID, "bspgpu_set_option: unknown option" );
 	}
 	return BSPGPU_OK;

@@ -127,6 +127,11 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 				if( !brush_solid[ b ] ) continue;
 				BrushRef r;
 				r.first_side = brushes[ b ].first_side; r.num_sides = brushes[ b ].num_sides;
+				/* a solid brush without sides: the reference's side loop (bsp.cc:127) does not run, the brush
+				 * never hits and `starts_inside` stays true.  One synthetic side with a zero normal and d = 0
+				 * (appended after the file's sides) does exactly that: start_dist and end_dist are 0 (or NaN for
+				 * non-finite input), so the side is skipped or crosses out of range -- no hit, inside kept. */
+				if( r.num_sides == 0 ) { r.first_side = L.num_brush_sides; r.num_sides = 1; }
 				r.brush = ( int32_t ) b; r.reserved = 0;
 				orefs.push_back( r );
 			}
@@ -138,14 +143,15 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	}
 
 	MapImageLayout & lay = out.layout;
-	lay.num_nodes = num_nodes; lay.num_refs = ( uint32_t ) orefs.size(); lay.num_sides = L.num_brush_sides;
+	const uint32_t num_sides_out = L.num_brush_sides + 1;   /* + the synthetic zero side */
+	lay.num_nodes = num_nodes; lay.num_refs = ( uint32_t ) orefs.size(); lay.num_sides = num_sides_out;
 	lay.tree_depth = tree_depth;
 	lay.off_nodes = 0;
 	lay.off_refs = align_up( lay.off_nodes + ( uint64_t ) num_nodes * sizeof( NodeRec ), kSectionAlign );
 	lay.off_sides = align_up( lay.off_refs + ( uint64_t ) orefs.size() * sizeof( BrushRef ), kSectionAlign );
-	lay.staged_bytes = align_up( lay.off_sides + ( uint64_t ) L.num_brush_sides * sizeof( SideRec ), kSectionAlign );
+	lay.staged_bytes = align_up( lay.off_sides + ( uint64_t ) num_sides_out * sizeof( SideRec ), kSectionAlign );
 	lay.off_side_plane = lay.staged_bytes;
-	lay.total_bytes = align_up( lay.off_side_plane + ( uint64_t ) L.num_brush_sides * sizeof( uint32_t ), kSectionAlign );
+	lay.total_bytes = align_up( lay.off_side_plane + ( uint64_t ) num_sides_out * sizeof( uint32_t ), kSectionAlign );
 	if( lay.total_bytes == 0 ) lay.total_bytes = kSectionAlign;
 
 	out.image.assign( lay.total_bytes, 0 );
@@ -158,6 +164,8 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 		osides[ s ].nx = pl.n[ 0 ]; osides[ s ].ny = pl.n[ 1 ]; osides[ s ].nz = pl.n[ 2 ]; osides[ s ].d = pl.d;
 		oside_plane[ s ] = sides[ s ].plane;
 	}
+	osides[ L.num_brush_sides ].nx = osides[ L.num_brush_sides ].ny = osides[ L.num_brush_sides ].nz = osides[ L.num_brush_sides ].d = 0.0f;
+	oside_plane[ L.num_brush_sides ] = 0;
 	return BSPGPU_OK;
 }
 

@@ -193,6 +193,169 @@ BSPK_HD void trace_one( const Map & map, const Ray & r, HitState & h ) {
 	}
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Resumable per-lane state machine: the same walk as trace_one, cut into two kinds of steps
+ * so that a warp can run "node steps" and "side steps" in separate, bounded phases and pick
+ * the phase most of its lanes are waiting for (trace_kernels.cuh).  Both phases can stop after
+ * any number of steps and resume later without changing one arithmetic operation or its order.
+ *
+ * Differences from trace_one that do not touch the arithmetic:
+ *  - stack entries carry their interval explicitly {node, tmin, tmax} (16 B, one 128-bit local
+ *    load/store), so far children that are empty leaves are never pushed, a straddle whose
+ *    near child is an empty leaf continues straight into the far child, and a pop is one load;
+ *  - the step bodies are written as selects over predicates (same comparisons as the
+ *    reference, evaluated unconditionally) so that lanes of a warp do not diverge inside a step;
+ *    rare events (brush end, leaf end, pop, next brush reference) are short separate blocks.
+ * ------------------------------------------------------------------------------------------ */
+
+enum LaneMode { kLaneIdle = 0, kLaneNode = 1, kLaneLeaf = 2, kLaneDone = 3 };
+
+struct alignas( 16 ) StackEntry16 {
+	int32_t node;
+	float tmin, tmax;
+	int32_t pad;
+};
+
+struct Lane {
+	Ray r;
+	float tmin, tmax;     /* current interval (the tmin/tmax arguments of bsp.cc:205) */
+	int32_t node;         /* kLaneNode: node to visit next */
+	int32_t sp;           /* stack height */
+	int32_t mode;
+	HitState h;
+	/* cursor inside a leaf (kLaneLeaf) */
+	uint32_t ri;          /* brush reference being clipped (or to be fetched when need_ref) */
+	uint32_t s, s_end;    /* side range still to test */
+	int32_t brush;
+	bool last_ref, need_ref;
+	BrushClip b;
+};
+
+BSPK_HD void lane_start( Lane & l, float sx, float sy, float sz, float ex, float ey, float ez ) {
+	l.r.sx = sx; l.r.sy = sy; l.r.sz = sz;
+	l.r.dx = ex - sx; l.r.dy = ey - sy; l.r.dz = ez - sz;      /* bsp.cc:261 */
+	hit_init( l.h );                                            /* bsp.cc:256-257 */
+	l.tmin = 0.0f; l.tmax = 1.0f; l.node = 0; l.sp = 0;         /* bsp.cc:263 */
+	l.mode = kLaneNode;
+	l.need_ref = false;
+}
+
+/* move to child reference `next` (node, or leaf with solid brushes) */
+BSPK_HD void lane_goto( Lane & l, int32_t next ) {
+	if( next >= 0 ) { l.node = next; l.mode = kLaneNode; }
+	else { l.ri = ( uint32_t ) ~next; l.need_ref = true; l.mode = kLaneLeaf; }
+}
+
+/* next pending far side = the second recursive call (bsp.cc:250-252), or Done when none is left */
+BSPK_HD void lane_pop( Lane & l, const StackEntry16 * stack ) {
+	if( l.sp == 0 ) { l.mode = kLaneDone; return; }
+	l.sp--;
+	const StackEntry16 e = stack[ l.sp ];
+	l.tmin = e.tmin; l.tmax = e.tmax;
+	lane_goto( l, e.node );
+}
+
+/* one trace_seg_tree step (bsp.cc:213-252) */
+template< class Map >
+BSPK_HD void lane_node_step( const Map & map, Lane & l, StackEntry16 * stack ) {
+	float nx, ny, nz, d; int32_t c0, c1;
+	map.node( l.node, nx, ny, nz, d, c0, c1 );
+	const float denom = dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );                /* :220 */
+	const float dist = -( dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d );        /* :221 */
+	const float u = dist / denom;                                                  /* :227 */
+	const bool in_range = denom != 0.0f && u >= 0.0f && u <= l.tmax;               /* :226,:232 */
+	const bool flip = in_range && u < l.tmin;                                      /* :235 */
+	const bool both = in_range && !( u < l.tmin );                                 /* :238 */
+	const bool near_child = ( dist > 0.0f ) != flip;                               /* :222,:236 */
+	const int32_t cn = near_child ? c1 : c0;                                       /* children[ near ] */
+	const int32_t cf = near_child ? c0 : c1;                                       /* children[ !near ] */
+	const bool far_work = both && cf != kEmptyLeaf;
+	if( cn != kEmptyLeaf ) {
+		if( far_work ) {                                                           /* far side later, over [u, tmax] (:251) */
+			StackEntry16 e; e.node = cf; e.tmin = u; e.tmax = l.tmax; e.pad = 0;
+			stack[ l.sp ] = e; l.sp++;
+		}
+		if( both ) l.tmax = u;                                                     /* near side over [tmin, u] (:248) */
+		lane_goto( l, cn );
+	}
+	else if( far_work ) { l.tmin = u; lane_goto( l, cf ); }                        /* near side is an empty leaf: nothing to do there */
+	else lane_pop( l, stack );
+}
+
+/* fetch brush reference l.ri and reset the clip state (bsp.cc:122-125) */
+template< class Map >
+BSPK_HD void lane_load_ref( const Map & map, Lane & l ) {
+	uint32_t first, nraw;
+	map.ref( l.ri, first, nraw, l.brush );
+	l.last_ref = ( nraw & kLastRef ) != 0;
+	l.s = first; l.s_end = first + ( nraw & ~kLastRef );
+	l.b.tfar = l.tmin; l.b.tnear = l.tmax; l.b.far_side = -1; l.b.hit = false; l.b.starts_inside = true;
+	l.need_ref = false;
+}
+
+/* one iteration of trace_seg_brush's side loop (bsp.cc:128-165) as selects; returns false when
+ * the brush is rejected (:135).  Flatten guarantees every referenced brush has >= 1 side. */
+BSPK_HD bool lane_side_step( Lane & l, float ex, float ey, float ez, float nx, float ny, float nz, float d ) {
+	const float start_dist = dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d;        /* :131 */
+	const float end_dist = dot3( ex, ey, ez, nx, ny, nz ) - d;                      /* :132 */
+	const float denom = -dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );               /* :141 */
+	const float t = start_dist / denom;                                             /* :142 */
+	const bool rejected = start_dist > 0.0f && end_dist > 0.0f;                     /* :135 */
+	const bool behind = start_dist <= 0.0f && end_dist <= 0.0f;                     /* :137 */
+	const bool crossing = !rejected && !behind;
+	const bool entering = start_dist >= 0.0f;
+	if( crossing && entering ) l.b.starts_inside = false;                           /* :139 */
+	const bool in_range = crossing && t >= l.tmin && t <= l.tmax;                   /* :144 */
+	const bool raise_far = in_range && entering && t >= l.b.tfar;                   /* :147-148 */
+	const bool lower_near = in_range && !entering && t <= l.b.tnear;                /* :154 */
+	if( raise_far ) { l.b.tfar = t; l.b.far_side = ( int32_t ) l.s; }
+	if( lower_near ) l.b.tnear = t;
+	if( raise_far || lower_near ) l.b.hit = true;
+	return !rejected;
+}
+
+/* up to `max_steps` node steps; stops early when the lane leaves node mode */
+template< class Map >
+BSPK_HD void lane_node_phase( const Map & map, Lane & l, StackEntry16 * stack, uint32_t max_steps ) {
+	while( l.mode == kLaneNode && max_steps-- ) lane_node_step( map, l, stack );
+}
+
+/* up to `max_steps` side steps, moving through the leaf's brushes */
+template< class Map >
+BSPK_HD void lane_leaf_phase( const Map & map, Lane & l, const StackEntry16 * stack, uint32_t max_steps ) {
+	/* end = start + dir * tmax (bsp.cc:121); tmax is the leaf interval's and is constant inside a leaf */
+	float ex = l.r.sx + l.r.dx * l.tmax, ey = l.r.sy + l.r.dy * l.tmax, ez = l.r.sz + l.r.dz * l.tmax;
+	while( l.mode == kLaneLeaf && max_steps-- ) {
+		if( l.need_ref ) lane_load_ref( map, l );
+		float nx, ny, nz, d;
+		map.side( l.s, nx, ny, nz, d );
+		const bool alive = lane_side_step( l, ex, ey, ez, nx, ny, nz, d );
+		l.s++;
+		if( alive && l.s != l.s_end ) continue;
+		/* brush over (rejected, or side loop complete) */
+		if( alive ) brush_finish( l.b, l.brush, l.h );                              /* bsp.cc:169-182 + :197-200 */
+		if( !l.last_ref ) { l.ri++; l.need_ref = true; continue; }
+		/* leaf over: a hit ends the whole trace (bsp.cc:206), otherwise the next pending far side */
+		if( l.h.hit ) { l.mode = kLaneDone; break; }
+		lane_pop( l, stack );
+		ex = l.r.sx + l.r.dx * l.tmax; ey = l.r.sy + l.r.dy * l.tmax; ez = l.r.sz + l.r.dz * l.tmax;
+	}
+}
+
+/* trace_one written with the resumable phases (budgets make no difference to the result) */
+template< class Map, int kStack >
+BSPK_HD void trace_one_phased( const Map & map, float sx, float sy, float sz, float ex, float ey, float ez,
+                               uint32_t node_budget, uint32_t side_budget, Ray & r_out, HitState & h_out ) {
+	StackEntry16 stack[ kStack ];
+	Lane l;
+	lane_start( l, sx, sy, sz, ex, ey, ez );
+	while( l.mode != kLaneDone ) {
+		lane_node_phase( map, l, stack, node_budget );
+		lane_leaf_phase( map, l, stack, side_budget );
+	}
+	r_out = l.r; h_out = l.h;
+}
+
 /* BSP::position_to_leaf (bsp.cc:273-286) on the flattened nodes; returns the file's leaf index */
 template< class Map >
 BSPK_HD int32_t point_leaf( const Map & map, float px, float py, float pz ) {

@@ -42,7 +42,9 @@ struct TraceParams {
 	uint32_t n;
 	uint32_t block_segs;              /* segments a warp claims per global atomic */
 	uint32_t refill;                  /* idle lanes that trigger a refill (1..32) */
-	uint32_t max_steps;               /* node steps per lane per round (bounds divergence) */
+	uint32_t max_steps;               /* node steps per lane per node phase (bounds divergence) */
+	uint32_t side_steps;              /* side steps per lane per leaf phase */
+	uint32_t leaf_threshold;          /* lanes waiting in a leaf that make the warp run a leaf phase */
 	unsigned long long * next;        /* work counter, zeroed before launch */
 	unsigned long long * hits;        /* accumulated hit count */
 };
@@ -98,19 +100,38 @@ __device__ __forceinline__ void st_stream4( void * p, float a, float b, float c,
 
 /* ---------------------------------------------------------------- map accessors */
 
+/* explicit ld.shared through 32-bit shared-window addresses: the generic->shared conversion of an
+ * `extern __shared__` pointer costs four uniform-datapath instructions at every load site */
+__device__ __forceinline__ float4 lds128( uint32_t addr ) {
+	float4 v;
+	asm volatile( "ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"( v.x ), "=f"( v.y ), "=f"( v.z ), "=f"( v.w ) : "r"( addr ) );
+	return v;
+}
+__device__ __forceinline__ int2 lds64i( uint32_t addr ) {
+	int2 v;
+	asm volatile( "ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"( v.x ), "=r"( v.y ) : "r"( addr ) );
+	return v;
+}
+__device__ __forceinline__ uint4 lds128u( uint32_t addr ) {
+	uint4 v;
+	asm volatile( "ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"( v.x ), "=r"( v.y ), "=r"( v.z ), "=r"( v.w ) : "r"( addr ) );
+	return v;
+}
+
 struct SmemAllMap {
-	const NodeRec * nodes; const BrushRef * refs; const SideRec * sides;   /* shared memory */
+	uint32_t nodes, refs, sides;   /* shared-window byte addresses of the three sections */
 	__device__ __forceinline__ void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const {
-		const float4 p = *reinterpret_cast< const float4 * >( &nodes[ i ] );
-		const int2 c = *reinterpret_cast< const int2 * >( &nodes[ i ].child[ 0 ] );
+		const uint32_t a = nodes + ( ( uint32_t ) i << 5 );
+		const float4 p = lds128( a );
+		const int2 c = lds64i( a + 16 );
 		nx = p.x; ny = p.y; nz = p.z; d = p.w; c0 = c.x; c1 = c.y;
 	}
 	__device__ __forceinline__ void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const {
-		const uint4 r = *reinterpret_cast< const uint4 * >( &refs[ i ] );
+		const uint4 r = lds128u( refs + ( i << 4 ) );
 		first = r.x; nraw = r.y; brush = ( int32_t ) r.z;
 	}
 	__device__ __forceinline__ void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const {
-		const float4 p = *reinterpret_cast< const float4 * >( &sides[ i ] );
+		const float4 p = lds128( sides + ( i << 4 ) );
 		nx = p.x; ny = p.y; nz = p.z; d = p.w;
 	}
 };
@@ -138,13 +159,14 @@ struct GlobalMap {
 };
 
 struct SmemTopMap {
-	const NodeRec * top;   /* shared memory: nodes [0, top_nodes) */
+	uint32_t top;          /* shared-window byte address of nodes [0, top_nodes) */
 	uint32_t top_nodes;
 	GlobalMap g;
 	__device__ __forceinline__ void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const {
 		if( ( uint32_t ) i < top_nodes ) {
-			const float4 p = *reinterpret_cast< const float4 * >( &top[ i ] );
-			const int2 c = *reinterpret_cast< const int2 * >( &top[ i ].child[ 0 ] );
+			const uint32_t a = top + ( ( uint32_t ) i << 5 );
+			const float4 p = lds128( a );
+			const int2 c = lds64i( a + 16 );
 			nx = p.x; ny = p.y; nz = p.z; d = p.w; c0 = c.x; c1 = c.y;
 		}
 		else g.node( i, nx, ny, nz, d, c0, c1 );
@@ -189,12 +211,12 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TracePa
 	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
 	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
 	if constexpr( kMode == kSmemAll ) {
-		map.nodes = reinterpret_cast< const NodeRec * >( smem );
-		map.refs = reinterpret_cast< const BrushRef * >( smem + p.off_refs );
-		map.sides = reinterpret_cast< const SideRec * >( smem + p.off_sides );
+		map.nodes = smem_u32( smem );
+		map.refs = map.nodes + ( uint32_t ) p.off_refs;
+		map.sides = map.nodes + ( uint32_t ) p.off_sides;
 	}
 	else if constexpr( kMode == kSmemTop ) {
-		map.top = reinterpret_cast< const NodeRec * >( smem );
+		map.top = smem_u32( smem );
 		map.top_nodes = p.top_nodes;
 		map.g.nodes = g_nodes; map.g.refs = g_refs; map.g.sides = g_sides;
 	}
@@ -303,6 +325,141 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TracePa
 	}
 
 	/* ---- K3: hit count, one atomic per warp */
+	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( kFull, my_hits, o );
+	if( lane == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
+}
+
+/* ---------------------------------------------------------------- K1/K2, phase-scheduled
+ *
+ * ncu on the round-based kernel above showed it issue-bound (88 % issue-active on rooms8) at
+ * only ~9 of 32 threads per instruction: lanes that reached an empty leaf idled through the
+ * whole brush loop of the few lanes that had brushes, and vice versa.  Here every lane is a
+ * small state machine (trace_core.h: Lane) that is either stepping nodes or stepping brush
+ * sides, empty leaves are popped on the spot, and each warp iteration runs ONE bounded phase:
+ * a leaf phase when at least `leaf_threshold` lanes wait in a leaf (or nobody can step nodes),
+ * otherwise a node phase.  Lanes of the other kind just keep their registers.  Finished lanes
+ * are re-filled as before. */
+template< int kMode, int kStack, int kMaxThreads >
+__global__ void __launch_bounds__( kMaxThreads ) trace_phased( const TraceParams p ) {
+	extern __shared__ __align__( 128 ) unsigned char smem[];
+	__shared__ __align__( 8 ) uint64_t stage_bar;
+
+	if( kMode != kGlobal && p.staged_bytes > 0 ) {
+		if( threadIdx.x == 0 ) {
+			mbar_init( &stage_bar, 1 );
+			mbar_fence_init();
+		}
+		__syncthreads();
+		if( threadIdx.x == 0 ) {
+			mbar_expect_tx( &stage_bar, p.staged_bytes );
+			const uint32_t kChunk = 32768;
+			for( uint32_t off = 0; off < p.staged_bytes; off += kChunk ) {
+				const uint32_t sz = min( kChunk, p.staged_bytes - off );
+				bulk_g2s( smem + off, p.image + off, sz, &stage_bar );
+			}
+		}
+		mbar_wait( &stage_bar, 0 );
+	}
+
+	typename MapOf< kMode >::type map;
+	const NodeRec * g_nodes = reinterpret_cast< const NodeRec * >( p.image );
+	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
+	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
+	if constexpr( kMode == kSmemAll ) {
+		map.nodes = smem_u32( smem );
+		map.refs = map.nodes + ( uint32_t ) p.off_refs;
+		map.sides = map.nodes + ( uint32_t ) p.off_sides;
+	}
+	else if constexpr( kMode == kSmemTop ) {
+		map.top = smem_u32( smem );
+		map.top_nodes = p.top_nodes;
+		map.g.nodes = g_nodes; map.g.refs = g_refs; map.g.sides = g_sides;
+	}
+	else {
+		map.nodes = g_nodes; map.refs = g_refs; map.sides = g_sides;
+	}
+	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
+
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = ( 1u << lane ) - 1u;
+	const unsigned kFull = 0xffffffffu;
+
+	uint32_t blk_next = 0, blk_end = 0;   /* warp-private block of claimed segments (warp-uniform) */
+	bool more_work = true;
+
+	Lane l;
+	l.mode = kLaneIdle;
+	l.r.sx = l.r.sy = l.r.sz = l.r.dx = l.r.dy = l.r.dz = 0.0f;
+	l.tmin = 0.0f; l.tmax = 1.0f; l.node = 0; l.sp = 0;
+	hit_init( l.h );
+	l.ri = l.s = l.s_end = 0; l.brush = -1; l.last_ref = false; l.need_ref = false;
+	l.b.tfar = l.b.tnear = 0.0f; l.b.far_side = -1; l.b.hit = false; l.b.starts_inside = true;
+	StackEntry16 stack[ kStack ];
+	uint32_t seg = 0, my_hits = 0;
+
+	for( ;; ) {
+		/* ---- warp-level work fetch + compaction */
+		const unsigned idle = __ballot_sync( kFull, l.mode == kLaneIdle );
+		const unsigned n_idle = __popc( idle );
+		if( more_work && n_idle >= p.refill ) {
+			if( blk_next == blk_end ) {
+				unsigned long long b = 0;
+				if( lane == 0 ) b = atomicAdd( p.next, ( unsigned long long ) p.block_segs );
+				b = __shfl_sync( kFull, b, 0 );
+				if( b >= ( unsigned long long ) p.n ) more_work = false;
+				else {
+					blk_next = ( uint32_t ) b;
+					blk_end = ( uint32_t ) min( b + ( unsigned long long ) p.block_segs, ( unsigned long long ) p.n );
+				}
+			}
+			if( more_work ) {
+				const uint32_t avail = blk_end - blk_next;
+				const uint32_t rank = __popc( idle & lt_mask );
+				if( l.mode == kLaneIdle && rank < avail ) {
+					seg = blk_next + rank;
+					if( p.segs24 ) {
+						const float2 * sp24 = p.segs24 + ( size_t ) seg * 3;
+						const float2 a = ld_stream2( sp24 ), b2 = ld_stream2( sp24 + 1 ), c = ld_stream2( sp24 + 2 );
+						lane_start( l, a.x, a.y, b2.x, b2.y, c.x, c.y );
+					}
+					else {
+						const float4 a = ld_stream4( p.segs + ( size_t ) seg * 2 );
+						const float4 b4 = ld_stream4( p.segs + ( size_t ) seg * 2 + 1 );
+						lane_start( l, a.x, a.y, a.z, b4.x, b4.y, b4.z );
+					}
+				}
+				blk_next += min( n_idle, avail );
+			}
+		}
+
+		/* ---- pick the phase most lanes are waiting for */
+		const unsigned in_node = __ballot_sync( kFull, l.mode == kLaneNode );
+		const unsigned in_leaf = __ballot_sync( kFull, l.mode == kLaneLeaf );
+		if( ( in_node | in_leaf ) == 0u ) {
+			if( !more_work ) break;
+			continue;
+		}
+		if( in_node == 0u || ( uint32_t ) __popc( in_leaf ) >= p.leaf_threshold ) {
+			if( l.mode == kLaneLeaf ) lane_leaf_phase( map, l, stack, p.side_steps );
+		}
+		else {
+			if( l.mode == kLaneNode ) lane_node_phase( map, l, stack, p.max_steps );
+		}
+
+		/* ---- retire finished segments */
+		if( l.mode == kLaneDone ) {
+			const ResultRec o = make_result( l.h, side_plane );
+			if( p.out ) st_stream4( p.out + seg, o.t, __int_as_float( o.plane ), __int_as_float( o.brush ), __uint_as_float( o.flags ) );
+			if( p.pos ) {
+				float px, py, pz;
+				make_pos( l.r, l.h, px, py, pz );                               /* bsp.cc:265-267 */
+				st_stream4( p.pos + seg, px, py, pz, l.h.t );
+			}
+			my_hits += ( uint32_t ) l.h.hit;
+			l.mode = kLaneIdle;
+		}
+	}
+
 	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( kFull, my_hits, o );
 	if( lane == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
 }

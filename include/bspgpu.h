@@ -105,7 +105,10 @@ enum {
 	BSPGPU_OPT_CHUNK_SEGMENTS = 5,  /* host-pointer path: segments per pipelined H2D/kernel/D2H chunk */
 	BSPGPU_OPT_REFILL = 6,          /* persistent-warp refill threshold (idle lanes before a warp fetches work) */
 	BSPGPU_OPT_MAX_STEPS = 7,       /* node steps a lane takes per round before the warp re-converges */
-	BSPGPU_OPT_BLOCK_SEGS = 8       /* consecutive segments a warp claims per global atomic (multiple of 32) */
+	BSPGPU_OPT_BLOCK_SEGS = 8,      /* consecutive segments a warp claims per global atomic (multiple of 32) */
+	BSPGPU_OPT_SCHEDULER = 9,       /* 0 = phase-scheduled lanes (default), 1 = round-based while-while kernel */
+	BSPGPU_OPT_SIDE_STEPS = 10,     /* brush-side steps a lane takes per leaf phase */
+	BSPGPU_OPT_LEAF_THRESHOLD = 11  /* lanes waiting in a leaf that make a warp run a leaf phase (1..32) */
 };
 
 typedef struct bspgpu_info {
@@ -135,6 +138,9 @@ int bspgpu_trace( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result * o
 int bspgpu_trace_pos( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result * out, bspgpu_pos * pos, unsigned flags );
 /* number of hits of the last completed trace on this handle (device-side reduction) */
 int bspgpu_hit_count( bspgpu_t * h, uint64_t * hits );
+/* same counter copied (8 bytes, async on the handle's stream) into caller-owned DEVICE memory, so a
+ * multi-GPU launcher can all-reduce it (NCCL) without a host round trip */
+int bspgpu_hit_count_device( bspgpu_t * h, void * dev_u64 );
 
 /* ---- batched BSP::position_to_leaf (bsp.cc:273-286): pts = 3 floats each (stride in floats), leaf = leaves-lump index ---- */
 int bspgpu_leaf( bspgpu_t * h, const float * pts, uint32_t stride, uint64_t n, int32_t * leaf, unsigned flags );

@@ -160,24 +160,29 @@ double bspref_trace_mt( void * h, const float * segs, uint64_t stride, uint64_t 
 		return -2.0; /* the reference queue cannot be resized or torn down */
 	}
 
+	/* work_queue.cc:78 asserts jobs_queued < 256, so work is handed out in rounds of <= 255 jobs, each
+	 * followed by workqueue_exhaust (the caller helps, work_queue.cc:91-98).  A round holds a whole
+	 * multiple of the thread count so every thread gets the same number of ~16k-segment jobs. */
 	static ChunkJob jobs[ 255 ];
-	const uint64_t max_jobs = 255; /* work_queue.cc:78 asserts jobs_queued < 256 */
-	uint64_t njobs = n < max_jobs ? n : max_jobs;
-	if( njobs == 0 ) return 0.0;
-	const uint64_t per = ( n + njobs - 1 ) / njobs;
+	if( n == 0 ) return 0.0;
+	const uint64_t per_round = nthreads <= 255 ? ( 255 / nthreads ) * ( uint64_t ) nthreads : 255;
+	uint64_t chunk = ( n + per_round - 1 ) / per_round;
+	if( chunk > 16384 ) chunk = 16384;
+	if( chunk < 1 ) chunk = 1;
 
 	const SegView sv = { segs, stride, end_off };
 	const Outputs out = { hit, t, pos, plane_set };
 
 	const double t0 = now_s();
-	for( uint64_t j = 0; j < njobs; j++ ) {
-		const uint64_t first = j * per;
-		if( first >= n ) break;
-		const uint64_t count = ( first + per <= n ) ? per : n - first;
-		jobs[ j ] = { ( const BSP * ) h, sv, out, first, count };
-		workqueue_enqueue( &g_queue, chunk_job, &jobs[ j ] );
+	uint64_t queued = 0;
+	for( uint64_t first = 0; first < n; first += chunk ) {
+		const uint64_t count = ( first + chunk <= n ) ? chunk : n - first;
+		jobs[ queued ] = { ( const BSP * ) h, sv, out, first, count };
+		workqueue_enqueue( &g_queue, chunk_job, &jobs[ queued ] );
+		queued++;
+		if( queued == per_round ) { workqueue_exhaust( &g_queue ); queued = 0; }
 	}
-	workqueue_exhaust( &g_queue );
+	if( queued ) workqueue_exhaust( &g_queue );
 	return now_s() - t0;
 }
 

@@ -68,6 +68,26 @@ void hostsim_trace( void * h, const float * segs, uint64_t stride, uint64_t end_
 	}
 }
 
+/* same walk through the resumable node/leaf phases the persistent kernel runs, with small and
+ * varying step budgets so every suspend/resume point is exercised */
+void hostsim_trace_phased( void * h, const float * segs, uint64_t stride, uint64_t end_off, uint64_t n, ResultRec * out, float * pos4,
+                           uint32_t node_budget, uint32_t side_budget ) {
+	const Sim * s = ( const Sim * ) h;
+	for( uint64_t i = 0; i < n; i++ ) {
+		const float * a = segs + i * stride;
+		const float * b = a + end_off;
+		Ray r; HitState hs;
+		const uint32_t nb = node_budget ? node_budget : 1 + ( uint32_t ) ( i % 7 );
+		const uint32_t sb = side_budget ? side_budget : 1 + ( uint32_t ) ( ( i / 7 ) % 5 );
+		trace_one_phased< ImageMap, 64 >( s->view, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs );
+		if( out ) out[ i ] = make_result( hs, s->side_plane );
+		if( pos4 ) {
+			make_pos( r, hs, pos4[ 4 * i + 0 ], pos4[ 4 * i + 1 ], pos4[ 4 * i + 2 ] );
+			pos4[ 4 * i + 3 ] = hs.t;
+		}
+	}
+}
+
 void hostsim_leaf( void * h, const float * pts, uint64_t stride, uint64_t n, int32_t * leaf ) {
 	const Sim * s = ( const Sim * ) h;
 	for( uint64_t i = 0; i < n; i++ ) {

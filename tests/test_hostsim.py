@@ -1,0 +1,102 @@
+"""CPU build of the device trace core (bsp_b200/csrc/trace_core.h, test-only) against the
+oracle: checks the flattened image, the explicit-stack formulation and the resumable
+node/leaf phases the persistent kernel runs -- bit for bit, without a GPU."""
+import numpy as np
+import pytest
+
+from helpers import HostSim, bits, load_golden, mixed_segments
+
+
+def _check(res, pos, exp, exp_pos, what):
+    bad = (bits(res).reshape(-1, 4) != bits(exp).reshape(-1, 4)).any(axis=1)
+    assert not bad.any(), f"{what}: {int(bad.sum())} mismatches, first {int(np.nonzero(bad)[0][0])}"
+    badp = (bits(pos[:, :3]) != bits(exp_pos)).any(axis=1)
+    assert not badp.any(), f"{what}: {int(badp.sum())} pos mismatches"
+
+
+@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "city10k"])
+def test_core_matches_oracle(oracle_mod, maps, name):
+    m, _ = maps(name)
+    segs = mixed_segments(m, 100_000, 100_000, 50_000, 8192)
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    sim = HostSim(m)
+    res, pos = sim.trace(segs)
+    _check(res, pos, exp, exp_pos, f"{name} trace_one")
+    for budgets in ((0, 0), (1, 1), (1000, 1000), (3, 2)):     # (0,0) = per-segment varying budgets
+        res, pos = sim.trace(segs, budgets)
+        _check(res, pos, exp, exp_pos, f"{name} phased {budgets}")
+
+
+@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8"])
+def test_core_matches_golden_reference_outputs(name):
+    m, segs, hit, t, pos = load_golden(name)
+    res, p = HostSim(m).trace(segs, (0, 0))
+    assert np.array_equal((res["flags"] & 1).astype(np.uint8), hit)
+    assert np.array_equal(bits(res["t"]), bits(t))
+    assert np.array_equal(bits(p[:, :3]), bits(pos))
+
+
+def _odd_map():
+    """hand-laid map with the corner cases of the flattener: a solid brush WITHOUT sides, a leaf
+    listing only non-solid brushes, an unreachable node, a leaf listing the same brush twice."""
+    from tools import mapgen
+    box = mapgen._kat_box
+    brush_planes = [box(-16, 16, -16, 16, -16, 16), [], box(40, 60, -8, 8, -8, 8), box(-60, -40, -8, 8, -8, 8)]
+    brush_tex = [0, 0, 1, 0]           # brush 1: solid, zero sides; brush 2: non-solid
+    planes, brushes, sides = [], [], []
+    for bp, tex in zip(brush_planes, brush_tex):
+        brushes.append((len(sides), len(bp), tex))
+        for p in bp:
+            sides.append((len(planes), tex)); planes.append(p)
+    px0 = len(planes); planes.append((1, 0, 0, 0))
+    py0 = len(planes); planes.append((0, 1, 0, 0))
+    # n0{x=0: [n1, L2]}  n1{y=0: [L0, L1]}  n2 unreachable
+    nodes = [(px0, 1, -3), (py0, -1, -2), (px0, -1, -2)]
+    leaves = [(0, 3), (3, 1), (4, 3)]              # L0=[b0,b1,b0]  L1=[b2] (non-solid only)  L2=[b3,b1,b0]
+    lb = [0, 1, 0, 2, 3, 1, 0]
+    return mapgen._raw_map([(b"solid", 0, 1), (b"water", 0, 0x20)], planes, nodes, leaves, lb, brushes, sides)
+
+
+def test_odd_maps(oracle_mod):
+    from tools import seggen
+    m = _odd_map()
+    sim = HostSim(m)
+    lay = sim.layout()
+    assert lay["nodes"] == 2                       # the unreachable node is dropped
+    assert lay["refs"] == 6                        # the non-solid brush is filtered out of L1
+    rs = np.random.Generator(np.random.PCG64(5))
+    segs = np.zeros((50_000, 8), np.float32)
+    segs[:, 0:3] = rs.uniform(-80, 80, (50_000, 3)); segs[:, 4:7] = rs.uniform(-80, 80, (50_000, 3))
+    segs[:1000, 0:3] = np.round(segs[:1000, 0:3] / 16) * 16   # endpoints on brush / node planes
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    assert (exp["flags"] & 2).any()                # the side-less brush makes every tested trace "startsolid"
+    for budgets in (None, (0, 0), (1, 1)):
+        res, pos = sim.trace(segs, budgets)
+        _check(res, pos, exp, exp_pos, f"odd map {budgets}")
+
+
+def test_position_to_leaf_core(oracle_mod, maps):
+    from tools import mapgen, seggen
+    for name in ("kat1", "rooms8"):
+        m, _ = maps(name)
+        lo, hi = mapgen.seg_bounds(m)
+        pts = np.ascontiguousarray(seggen.uniform(3, 0, 50_000, lo, hi)[:, :4])
+        assert np.array_equal(HostSim(m).leaf(pts), oracle_mod.Port(m).leaf(pts))
+
+
+def test_flatten_rejects_broken_maps(maps):
+    import copy
+    m, _ = maps("kat1")
+    for field, idx, key, val, what in (
+            ("nodes", 0, "plane", 10_000, "plane"), ("nodes", 1, "children", (5, -2), "child"),
+            ("nodes", 1, "children", (0, -2), "reached twice"), ("leaves", 2, "num_brushes", 99, "leafbrushes"),
+            ("brushes", 1, "texture", 7, "texture"), ("brushes", 2, "num_sides", 1000, "sides"),
+            ("brush_sides", 3, "plane", 4000, "plane"), ("leaf_brushes", 0, None, 77, "brush")):
+        bad = copy.deepcopy(m)
+        arr = getattr(bad, field)
+        if key is None:
+            arr[idx] = val
+        else:
+            arr[key][idx] = val
+        with pytest.raises(ValueError, match=what):
+            HostSim(bad)

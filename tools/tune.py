@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--ctas", default="0")
     ap.add_argument("--top", default="98304")
     ap.add_argument("--block_segs", default="256")
+    ap.add_argument("--sched", default="0")
+    ap.add_argument("--side_steps", default="8")
+    ap.add_argument("--leaf_thr", default="12")
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     bsp_b200.build()
@@ -45,8 +48,10 @@ def main():
         g.generate(segs, 0, a.n, 1, 5, lo, hi, 1.0, 32.0)
     out = torch.empty((a.n, 4), dtype=torch.int32, device="cuda")
     ints = lambda s: [int(x) for x in s.split(",")]
-    for variant, threads, refill, steps, ctas, top, bs in itertools.product(
-            ints(a.variants), ints(a.threads), ints(a.refill), ints(a.steps), ints(a.ctas), ints(a.top), ints(a.block_segs)):
+    for variant, threads, refill, steps, ctas, top, bs, sched, ss, lt in itertools.product(
+            ints(a.variants), ints(a.threads), ints(a.refill), ints(a.steps), ints(a.ctas), ints(a.top), ints(a.block_segs),
+            ints(a.sched), ints(a.side_steps), ints(a.leaf_thr)):
+        g.set_option(9, sched); g.set_option(10, ss); g.set_option(11, lt)
         g.set_option(1, variant); g.set_option(2, threads); g.set_option(6, refill); g.set_option(7, steps)
         g.set_option(3, ctas); g.set_option(4, top); g.set_option(8, bs)
         try:
@@ -58,7 +63,7 @@ def main():
                 best = min(best, e0.elapsed_time(e1))
             inf = g.info()
             print(json.dumps({"map": a.map, "kind": a.kind, "n": a.n, "variant": inf["variant"], "threads": threads, "grid": inf["grid_ctas"],
-                              "smem": inf["smem_bytes"], "refill": refill, "max_steps": steps, "block_segs": bs, "top": top, "ms": round(best, 3),
+                              "smem": inf["smem_bytes"], "sched": sched, "refill": refill, "max_steps": steps, "side_steps": ss, "leaf_thr": lt, "block_segs": bs, "top": top, "ms": round(best, 3),
                               "Mtraces_s": round(a.n / best / 1e3, 1), "hits": g.hit_count()}), flush=True)
         except bsp_b200.BspGpuError as e:
             print(json.dumps({"variant": variant, "threads": threads, "error": str(e)}), flush=True)
