@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             print(" ".join(cmd)); print(r.stdout); print(r.stderr)
         if r.returncode:
             raise RuntimeError("nvcc failed building libbspgpu.so")
-    host_src = os.path.join(CSRC, "host", "bsp.cc")
+    host_src = os.path.join(CSRC, "host", "bsp_host.cc")
     if os.path.exists(host_src) and (force or _stale(LIB_HOST, deps + [LIB_GPU])):
         cmd = ["g++"] + CXX_FLAGS + ["-o", LIB_HOST, host_src, "-L" + HERE, "-lbspgpu", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,0 +1,68 @@
+/*
+ * tests/cpp/test_dropin.cc -- the reference-facing C++ interface, used the way the reference's
+ * own call site uses it (game_frame, reference bsp.cc:363-370): bsp_init, trace_seg per
+ * segment, plus the new batched trace_segs.  Checks the KAT-1 vectors captured from the
+ * unmodified reference.  usage: test_dropin <kat1.bsp>
+ */
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "../../bsp_b200/csrc/host/bsp_host.h"
+
+struct Kat { float s[ 3 ], e[ 3 ]; int hit; uint32_t t_bits; };
+
+static const Kat kat1[] = {
+	{ { 64, 0, 0 }, { -64, 0, 0 }, 1, 0x3F000000u }, { { -64, 0, 0 }, { 64, 0, 0 }, 1, 0x3EC00000u },
+	{ { 180, 0, 0 }, { 60, 0, 0 }, 1, 0x3ED55555u }, { { 180, 12, 0 }, { 60, 12, 0 }, 1, 0x3F000000u },
+	{ { 190, 0, 0 }, { 260, 0, 0 }, 1, 0x3F124925u }, { { 190, 0, 0 }, { 225, 0, 0 }, 0, 0x3F800000u },
+	{ { -10, 45, 0 }, { 207.5f, 210, 0 }, 1, 0x3F22E8BAu }, { { 200, 157, 3 }, { 100, 157, -5 }, 1, 0x3F11EB85u },
+	{ { 100, 158, 0 }, { 160, 156, 1 }, 1, 0x3EF564F6u }, { { 110, 40, 0 }, { 110, -40, 0 }, 1, 0x3E99999Au },
+	{ { 10, 0, 0 }, { -64, 0, 0 }, 0, 0x3F800000u }, { { 140, 36, 0 }, { 100, -4, 0 }, 1, 0x3F000000u },
+};
+
+static uint32_t bits( float f ) { uint32_t u; memcpy( &u, &f, 4 ); return u; }
+
+int main( int argc, char ** argv ) {
+	if( argc < 2 ) { fprintf( stderr, "usage: %s kat1.bsp\n", argv[ 0 ] ); return 2; }
+	BSP bsp;
+	bsp_init( &bsp, argv[ 1 ] );
+	int bad = 0;
+	const size_t n = sizeof( kat1 ) / sizeof( kat1[ 0 ] );
+
+	std::vector< Segment > segs( n );
+	for( size_t i = 0; i < n; i++ ) {
+		segs[ i ].start = glm::vec3( kat1[ i ].s[ 0 ], kat1[ i ].s[ 1 ], kat1[ i ].s[ 2 ] );
+		segs[ i ].end = glm::vec3( kat1[ i ].e[ 0 ], kat1[ i ].e[ 1 ], kat1[ i ].e[ 2 ] );
+		/* the reference call shape: one segment, one Intersection */
+		Intersection is;
+		const bool hit = bsp.trace_seg( segs[ i ].start, segs[ i ].end, is );
+		if( hit != ( kat1[ i ].hit != 0 ) || bits( is.t ) != kat1[ i ].t_bits || is.plane != nullptr ) {
+			printf( "trace_seg %zu: hit %d t %08x (want %d %08x)\n", i, ( int ) hit, bits( is.t ), kat1[ i ].hit, kat1[ i ].t_bits );
+			bad++;
+		}
+		if( !hit && ( is.pos.x != 0.0f || is.pos.y != 0.0f || is.pos.z != 0.0f ) ) { printf( "trace_seg %zu: pos not zero on a miss\n", i ); bad++; }
+	}
+
+	std::vector< TraceResult > res( n );
+	bsp.trace_segs( segs.data(), n, res.data() );
+	uint64_t hits = 0;
+	for( size_t i = 0; i < n; i++ ) {
+		hits += kat1[ i ].hit;
+		if( ( int ) ( res[ i ].flags & BSPGPU_HIT ) != kat1[ i ].hit || bits( res[ i ].t ) != kat1[ i ].t_bits ) {
+			printf( "trace_segs %zu: flags %u t %08x (want %d %08x)\n", i, res[ i ].flags, bits( res[ i ].t ), kat1[ i ].hit, kat1[ i ].t_bits );
+			bad++;
+		}
+	}
+	if( bsp.last_hit_count() != hits ) { printf( "hit count %llu, want %llu\n", ( unsigned long long ) bsp.last_hit_count(), ( unsigned long long ) hits ); bad++; }
+	if( res[ 0 ].plane != -1 || !( res[ 10 ].flags & BSPGPU_STARTSOLID ) ) { printf( "extension fields off\n" ); bad++; }
+
+	/* position_to_leaf (bsp.cc:273-286): x<0 -> leaf 0; x>0,y>50 -> leaf 1; x>0,y<50 -> leaf 2 */
+	if( &bsp.position_to_leaf( glm::vec3( -5, 0, 0 ) ) != &bsp.leaves[ 0 ] ) { printf( "leaf 0\n" ); bad++; }
+	if( &bsp.position_to_leaf( glm::vec3( 5, 60, 0 ) ) != &bsp.leaves[ 1 ] ) { printf( "leaf 1\n" ); bad++; }
+	if( &bsp.position_to_leaf( glm::vec3( 5, 40, 0 ) ) != &bsp.leaves[ 2 ] ) { printf( "leaf 2\n" ); bad++; }
+
+	bsp_destroy( &bsp );
+	printf( bad ? "FAILED %d\n" : "OK\n", bad );
+	return bad ? 1 : 0;
+}

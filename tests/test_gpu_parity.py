@@ -85,12 +85,13 @@ def test_parity_vs_oracle(native, maps, oracle_mod, mapname, variant):
 
 
 @pytest.mark.parametrize("refill,max_steps,threads", [(1, 1, 128), (32, 1000, 256), (8, 4, 1024), (16, 64, 512)])
-def test_scheduling_knobs_do_not_change_results(native, maps, oracle_mod, refill, max_steps, threads):
+@pytest.mark.parametrize("side_steps,leaf_thr", [(1, 1), (8, 16), (1000, 32)])
+def test_scheduling_knobs_do_not_change_results(native, maps, oracle_mod, refill, max_steps, threads, side_steps, leaf_thr):
     m, _ = maps("rooms8")
     segs = _segments(m, 100_000, 50_000, 50_000, 4096)
     exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
     g = native.BspGpu(m)
-    g.set_option(6, refill); g.set_option(7, max_steps); g.set_option(2, threads)
+    g.set_option(6, refill); g.set_option(7, max_steps); g.set_option(2, threads); g.set_option(10, side_steps); g.set_option(11, leaf_thr)
     res = g.trace(segs)
     _compare(res, None, exp, exp_pos, f"knobs {refill}/{max_steps}/{threads}")
     g.close()
@@ -207,4 +208,48 @@ def test_errors(native, maps):
     lib = native.load_library()
     assert lib.bspgpu_trace(g.h, None, 5, None, 0) < 0
     assert b"null" in lib.bspgpu_last_error()
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8"])
+def test_golden_reference_outputs(native, name):
+    """committed fixtures = outputs of the unmodified reference (tests/golden/make_golden.py)."""
+    from helpers import load_golden
+    m, segs, hit, t, pos = load_golden(name)
+    g = native.BspGpu(m)
+    p = np.zeros((len(segs), 4), np.float32)
+    res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=p)
+    assert np.array_equal((res["flags"] & 1).astype(np.uint8), hit)
+    assert np.array_equal(bits(res["t"]), bits(t))
+    assert np.array_equal(bits(p[:, :3]), bits(pos))
+    g.close()
+
+
+def test_both_schedulers_agree(native, maps, oracle_mod):
+    m, _ = maps("city10k")
+    segs = _segments(m, 100_000, 200_000, 50_000, 4096)
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    for sched in (0, 1):
+        g.set_option(9, sched)
+        res = g.trace(segs)
+        _compare(res, None, exp, exp_pos, f"scheduler {sched}")
+    g.close()
+
+
+def test_odd_map_on_gpu(native, oracle_mod):
+    """brush without sides, leaf with only non-solid brushes, unreachable node (see test_hostsim)."""
+    from test_hostsim import _odd_map
+    m = _odd_map()
+    rs = np.random.Generator(np.random.PCG64(5))
+    segs = np.zeros((50_000, 8), np.float32)
+    segs[:, 0:3] = rs.uniform(-80, 80, (50_000, 3)); segs[:, 4:7] = rs.uniform(-80, 80, (50_000, 3))
+    segs[:1000, 0:3] = np.round(segs[:1000, 0:3] / 16) * 16
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    for variant in (1, 2, 3):
+        g.set_option(1, variant)
+        pos = np.zeros((len(segs), 4), np.float32)
+        res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+        _compare(res, pos, exp, exp_pos, f"odd map variant {variant}")
     g.close()
