@@ -150,6 +150,28 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """best effort: run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node the GPU hangs off."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]                                  # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -277,7 +299,7 @@ def run_ours(a):
     g = bsp_b200.BspGpu(w["path"], device=local)
     stream = torch.cuda.Stream()
     g.set_stream(stream.cuda_stream)
-    for opt, val in ((2, a.threads), (6, a.refill), (7, a.max_steps), (1, a.variant), (4, a.top_bytes), (3, a.ctas), (8, a.block_segs)):
+    for opt, val in ((2, a.threads), (6, a.refill), (7, a.max_steps), (1, a.variant), (4, a.top_bytes), (3, a.ctas), (8, a.block_segs), (5, a.chunk)):
         if val is not None:
             g.set_option(opt, val)
 
@@ -336,26 +358,32 @@ def run_ours(a):
     total_segments = per_gpu * world * a.steps
     value = total_segments / (elapsed_ms * 1e-3)
 
-    # ---------------- e2e: host buffers through the same public call
+    # ---------------- e2e: host buffers through the same public call.  Segments are handed over as the
+    # reference's own argument layout -- two packed glm::vec3 = 24 bytes (BSP::trace_seg, bsp.h:210;
+    # BSP::trace_segs in the C++ mirror) -- results come back as 16-byte TraceResults.
     e2e_n = min(per_gpu, a.e2e_segments)
     lib = bsp_b200.load_library()
-    h_in_ptr = lib.bspgpu_host_alloc(e2e_n * 32)
+    bind_to_gpu_numa_node(local)
+    h_in_ptr = lib.bspgpu_host_alloc(e2e_n * 24)
     h_out_ptr = lib.bspgpu_host_alloc(e2e_n * 16)
     if not h_in_ptr or not h_out_ptr:
         raise SystemExit("bench.py: pinned allocation failed")
     import ctypes as C
-    h_in = np.ctypeslib.as_array((C.c_float * (e2e_n * 8)).from_address(h_in_ptr)).reshape(e2e_n, 8)
+    h_in = np.ctypeslib.as_array((C.c_float * (e2e_n * 6)).from_address(h_in_ptr)).reshape(e2e_n, 6)
     h_out = np.ctypeslib.as_array((C.c_uint32 * (e2e_n * 4)).from_address(h_out_ptr)).reshape(e2e_n, 4)
-    h_in[:] = segs[:e2e_n].cpu().numpy()
+    seg_host = segs[:e2e_n].cpu().numpy()
+    h_in[:, 0:3] = seg_host[:, 0:3]
+    h_in[:, 3:6] = seg_host[:, 4:7]
+    del seg_host
     h_res = h_out.view(bsp_b200.RESULT_DT).reshape(-1)
     e2e_steps = max(2, min(a.steps, 5))
     g.reset_stream()
     for _ in range(2):
-        g.trace(h_in, out=h_res)
+        g.trace(h_in, out=h_res, packed24=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        g.trace(h_in, out=h_res)                           # H2D + kernels + D2H, synchronous on return
+        g.trace(h_in, out=h_res, packed24=True)            # H2D + kernels + D2H, synchronous on return
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -366,6 +394,8 @@ def run_ours(a):
     dev_hits_prefix = int((out[:e2e_n, 3] & 1).sum().item())
     if e2e_hits != dev_hits_prefix:
         raise SystemExit(f"bench.py: host-path results differ from device-path results ({e2e_hits} vs {dev_hits_prefix} hits)")
+    if not np.array_equal(h_out[:: max(1, e2e_n // 65536)], out[:e2e_n: max(1, e2e_n // 65536)].cpu().numpy().view(np.uint32)):
+        raise SystemExit("bench.py: host-path results differ from device-path results")
 
     if rank == 0:
         clocks = sampler.stop() if sampler else None
@@ -409,7 +439,8 @@ def run_ours(a):
                          "hbm_stream_gbs": bpt["b_io"] * per_gpu / (mean_kernel_ms * 1e-3) / 1e9,
                          "note": "achieved = algorithmic bytes (map records the reference walk touches + 48 B segment/result I/O) per second; "
                                  "map bytes are served from shared memory / L1 / L2, only the I/O stream reaches HBM"},
-            "e2e": {"value": e2e_value, "unit": "traces/s", "h2d_bytes_per_step": e2e_n * 32, "d2h_bytes_per_step": e2e_n * 16,
+            "e2e": {"value": e2e_value, "unit": "traces/s", "h2d_bytes_per_step": e2e_n * 24, "d2h_bytes_per_step": e2e_n * 16,
+                    "layout": "24 B packed vec3 pairs in (the reference's trace_seg arguments), 16 B TraceResult out, pinned host memory, chunked 3-stream pipeline",
                     "segments_per_gpu_per_step": e2e_n, "steps": e2e_steps},
             "gpu_launches": launches_per_step * a.steps,
             "clocks": clocks,
@@ -443,6 +474,7 @@ def main():
     ap.add_argument("--top-bytes", type=int, default=None)
     ap.add_argument("--ctas", type=int, default=None)
     ap.add_argument("--block-segs", type=int, default=None)
+    ap.add_argument("--chunk", type=int, default=None, help="host path: segments per pipelined chunk")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -47,9 +47,14 @@ TraceKernel pick_threads( int threads, int sched ) {
 		if( threads <= 512 ) return trace_persistent< M, S, 512 >;
 		return trace_persistent< M, S, 1024 >;
 	}
-	if( threads <= 256 ) return trace_phased< M, S, 256 >;
-	if( threads <= 512 ) return trace_phased< M, S, 512 >;
-	return trace_phased< M, S, 1024 >;
+	if( sched == 2 ) {   /* experiment: 1536 threads per SM (<= 40 registers) */
+		if( threads <= 256 ) return trace_phased< M, S, 256, 6 >;
+		if( threads <= 512 ) return trace_phased< M, S, 512, 3 >;
+		return trace_phased< M, S, 768, 2 >;
+	}
+	if( threads <= 256 ) return trace_phased< M, S, 256, 1 >;
+	if( threads <= 512 ) return trace_phased< M, S, 512, 1 >;
+	return trace_phased< M, S, 1024, 1 >;
 }
 template< int M >
 TraceKernel pick_stack( int depth, int threads, int sched ) {
@@ -77,8 +82,14 @@ struct bspgpu {
 
 	/* options */
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 96 * 1024;
-	int64_t opt_chunk = 4ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;   /* 0 = per-variant default */
+	int64_t opt_chunk = 2ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;   /* 0 = per-variant default */
 	int64_t opt_sched = 0, opt_side_steps = 8, opt_leaf_threshold = 16;
+
+	/* launch configuration, recomputed only after an option changed */
+	bool cfg_valid = false;
+	TraceKernel cfg_kernel = nullptr;
+	int cfg_variant = 0, cfg_mode = 0, cfg_threads = 0, cfg_grid = 0;
+	uint32_t cfg_smem = 0, cfg_top_nodes = 0;
 
 	/* what the last trace did */
 	uint32_t last_variant = 0, last_threads = 0, last_grid = 0, last_smem = 0, last_launches = 0;
@@ -97,41 +108,48 @@ struct bspgpu {
 namespace {
 
 int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, bspgpu_result * d_out, bspgpu_pos * d_pos, cudaStream_t st ) {
-	/* variant */
-	int variant = ( int ) h->opt_variant;
-	const uint64_t smem_cap = ( uint64_t ) h->max_smem_optin > 1024 ? ( uint64_t ) h->max_smem_optin - 1024 : 0;
-	/* AUTO (measured on B200, profiles/): the whole map in shared memory when it fits; otherwise the read-only
-	 * global path -- for a few-MB map L1 already keeps the top of the tree resident and staging it buys nothing */
-	if( variant == BSPGPU_VARIANT_AUTO ) variant = h->lay.staged_bytes <= smem_cap ? BSPGPU_VARIANT_SMEM : BSPGPU_VARIANT_GLOBAL;
-	int mode; uint32_t smem = 0, top_nodes = 0;
-	if( variant == BSPGPU_VARIANT_SMEM ) {
-		if( h->lay.staged_bytes > smem_cap ) return fail( BSPGPU_E_INVALID, "SMEM variant: flattened map does not fit in shared memory" );
-		mode = kSmemAll; smem = ( uint32_t ) h->lay.staged_bytes;
-	}
-	else if( variant == BSPGPU_VARIANT_TOPTREE ) {
-		mode = kSmemTop;
-		uint64_t bytes = ( uint64_t ) h->opt_top_bytes;
-		if( bytes > smem_cap ) bytes = smem_cap;
-		const uint64_t all = ( uint64_t ) h->lay.num_nodes * sizeof( NodeRec );
-		if( bytes > all ) bytes = all;
-		top_nodes = ( uint32_t ) ( bytes / sizeof( NodeRec ) );
-		smem = top_nodes * ( uint32_t ) sizeof( NodeRec );
-	}
-	else mode = kGlobal;
+	if( !h->cfg_valid ) {
+		int variant = ( int ) h->opt_variant;
+		const uint64_t smem_cap = ( uint64_t ) h->max_smem_optin > 1024 ? ( uint64_t ) h->max_smem_optin - 1024 : 0;
+		/* AUTO (measured on B200, profiles/): the whole map in shared memory when it fits; otherwise the read-only
+		 * global path -- for a few-MB map L1 already keeps the top of the tree resident and staging it buys nothing */
+		if( variant == BSPGPU_VARIANT_AUTO ) variant = h->lay.staged_bytes <= smem_cap ? BSPGPU_VARIANT_SMEM : BSPGPU_VARIANT_GLOBAL;
+		int mode; uint32_t smem = 0, top_nodes = 0;
+		if( variant == BSPGPU_VARIANT_SMEM ) {
+			if( h->lay.staged_bytes > smem_cap ) return fail( BSPGPU_E_INVALID, "SMEM variant: flattened map does not fit in shared memory" );
+			mode = kSmemAll; smem = ( uint32_t ) h->lay.staged_bytes;
+		}
+		else if( variant == BSPGPU_VARIANT_TOPTREE ) {
+			mode = kSmemTop;
+			uint64_t bytes = ( uint64_t ) h->opt_top_bytes;
+			if( bytes > smem_cap ) bytes = smem_cap;
+			const uint64_t all = ( uint64_t ) h->lay.num_nodes * sizeof( NodeRec );
+			if( bytes > all ) bytes = all;
+			top_nodes = ( uint32_t ) ( bytes / sizeof( NodeRec ) );
+			smem = top_nodes * ( uint32_t ) sizeof( NodeRec );
+		}
+		else mode = kGlobal;
 
-	int threads = ( int ) h->opt_threads;
-	if( threads <= 0 ) threads = 1024;
-	threads = ( threads + 31 ) / 32 * 32;
-	if( threads > 1024 ) threads = 1024;
+		int threads = ( int ) h->opt_threads;
+		if( threads <= 0 ) threads = ( mode == kSmemAll ) ? 1024 : 256;   /* measured: 1 x 1024 with the map in smem, 5 x 256 otherwise */
+		threads = ( threads + 31 ) / 32 * 32;
+		if( threads > 1024 ) threads = 1024;
+		if( h->opt_sched == 2 && threads > 768 ) threads = 768;
 
-	TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched );
-	CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );
-	int ctas = ( int ) h->opt_ctas;
-	int occ = 0;
-	CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &occ, kernel, threads, smem ) );
-	if( occ < 1 ) return fail( BSPGPU_E_CUDA, "kernel does not fit on an SM with the requested block size / shared memory" );
-	if( ctas <= 0 || ctas > occ ) ctas = occ;
-	const int grid = h->sm_count * ctas;
+		TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched );
+		CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );
+		int ctas = ( int ) h->opt_ctas;
+		int occ = 0;
+		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &occ, kernel, threads, smem ) );
+		if( occ < 1 ) return fail( BSPGPU_E_CUDA, "kernel does not fit on an SM with the requested block size / shared memory" );
+		if( ctas <= 0 || ctas > occ ) ctas = occ;
+		h->cfg_kernel = kernel; h->cfg_variant = variant; h->cfg_mode = mode; h->cfg_threads = threads;
+		h->cfg_grid = h->sm_count * ctas; h->cfg_smem = smem; h->cfg_top_nodes = top_nodes;
+		h->cfg_valid = true;
+	}
+	TraceKernel kernel = h->cfg_kernel;
+	const int variant = h->cfg_variant, mode = h->cfg_mode, threads = h->cfg_threads, grid = h->cfg_grid;
+	const uint32_t smem = h->cfg_smem, top_nodes = h->cfg_top_nodes;
 
 	TraceParams p;
 	p.image = h->d_image;
@@ -436,6 +454,7 @@ int bspgpu_generate( bspgpu_t * h, const bspgpu_gen_desc * g, uint64_t first, ui
 
 int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_set_option: null handle" );
+	h->cfg_valid = false;
 	switch( option ) {
 		case BSPGPU_OPT_VARIANT: if( value < 0 || value > 3 ) return fail( BSPGPU_E_INVALID, "bad variant" ); h->opt_variant = value; break;
 		case BSPGPU_OPT_BLOCK_THREADS: h->opt_threads = value; break;

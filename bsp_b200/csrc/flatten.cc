@@ -136,7 +136,7 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 				orefs.push_back( r );
 			}
 			if( orefs.size() == first_ref ) { o.child[ k ] = kEmptyLeaf; continue; }
-			if( first_ref >= 0x7fffffffu ) { err = "too many leaf brush references"; return BSPGPU_E_MAP; }
+			if( orefs.size() >= 0x7ffffff0u ) { err = "too many leaf brush references"; return BSPGPU_E_MAP; }
 			orefs.back().num_sides |= kLastRef;
 			o.child[ k ] = ~( int32_t ) first_ref;
 		}

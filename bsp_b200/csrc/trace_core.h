@@ -208,7 +208,15 @@ BSPK_HD void trace_one( const Map & map, const Ray & r, HitState & h ) {
  *    rare events (brush end, leaf end, pop, next brush reference) are short separate blocks.
  * ------------------------------------------------------------------------------------------ */
 
-enum LaneMode { kLaneIdle = 0, kLaneNode = 1, kLaneLeaf = 2, kLaneDone = 3 };
+/* Lane state is packed so the step bodies stay short:
+ *   cur >= 0                  node mode: index of the node to visit next
+ *   kCurDone < cur < 0        leaf mode: ~cur = brush reference being clipped (the child encoding itself);
+ *                             s == s_end means "fetch that reference first"
+ *   cur == kCurDone / kCurIdle  finished (result not yet written) / no segment                              */
+static const int32_t kCurIdle = INT32_MIN;        /* == kEmptyLeaf, which is never a live state */
+static const int32_t kCurDone = INT32_MIN + 1;
+static const uint32_t kBrushHit = 1u, kBrushInside = 2u, kBrushLastRef = 4u;
+static const uint32_t kHitFlag = 1u, kStartSolidFlag = 2u;
 
 struct alignas( 16 ) StackEntry16 {
 	int32_t node;
@@ -219,125 +227,136 @@ struct alignas( 16 ) StackEntry16 {
 struct Lane {
 	Ray r;
 	float tmin, tmax;     /* current interval (the tmin/tmax arguments of bsp.cc:205) */
-	int32_t node;         /* kLaneNode: node to visit next */
+	int32_t cur;
 	int32_t sp;           /* stack height */
-	int32_t mode;
-	HitState h;
-	/* cursor inside a leaf (kLaneLeaf) */
-	uint32_t ri;          /* brush reference being clipped (or to be fetched when need_ref) */
+	/* running result (bis.hit / bis.is.t, bsp.h:149-154, + extensions) */
+	float ht;
+	uint32_t hflags;      /* kHitFlag | kStartSolidFlag */
+	int32_t hside, hbrush;
+	/* cursor inside a leaf */
 	uint32_t s, s_end;    /* side range still to test */
 	int32_t brush;
-	bool last_ref, need_ref;
-	BrushClip b;
+	uint32_t bflags;      /* kBrushHit | kBrushInside | kBrushLastRef */
+	float tfar, tnear;
+	int32_t far_side;
 };
+
+BSPK_HD bool lane_in_node( const Lane & l ) { return l.cur >= 0; }
+BSPK_HD bool lane_in_leaf( const Lane & l ) { return ( uint32_t ) l.cur > ( uint32_t ) kCurDone; }   /* negative, above kCurDone */
+BSPK_HD bool lane_done( const Lane & l ) { return l.cur == kCurDone; }
+BSPK_HD bool lane_idle( const Lane & l ) { return l.cur == kCurIdle; }
 
 BSPK_HD void lane_start( Lane & l, float sx, float sy, float sz, float ex, float ey, float ez ) {
 	l.r.sx = sx; l.r.sy = sy; l.r.sz = sz;
 	l.r.dx = ex - sx; l.r.dy = ey - sy; l.r.dz = ez - sz;      /* bsp.cc:261 */
-	hit_init( l.h );                                            /* bsp.cc:256-257 */
-	l.tmin = 0.0f; l.tmax = 1.0f; l.node = 0; l.sp = 0;         /* bsp.cc:263 */
-	l.mode = kLaneNode;
-	l.need_ref = false;
+	l.ht = 1.0f; l.hflags = 0; l.hside = -1; l.hbrush = -1;      /* bsp.cc:256-257 */
+	l.tmin = 0.0f; l.tmax = 1.0f; l.cur = 0; l.sp = 0;          /* bsp.cc:263 */
+	l.s = 0; l.s_end = 0;
 }
 
-/* move to child reference `next` (node, or leaf with solid brushes) */
-BSPK_HD void lane_goto( Lane & l, int32_t next ) {
-	if( next >= 0 ) { l.node = next; l.mode = kLaneNode; }
-	else { l.ri = ( uint32_t ) ~next; l.need_ref = true; l.mode = kLaneLeaf; }
+BSPK_HD void lane_hit_state( const Lane & l, HitState & h ) {
+	h.t = l.ht; h.hit = ( l.hflags & kHitFlag ) ? 1 : 0; h.startsolid = ( l.hflags & kStartSolidFlag ) ? 1 : 0;
+	h.far_side = l.hside; h.brush = l.hbrush;
 }
 
-/* next pending far side = the second recursive call (bsp.cc:250-252), or Done when none is left */
-BSPK_HD void lane_pop( Lane & l, const StackEntry16 * stack ) {
-	if( l.sp == 0 ) { l.mode = kLaneDone; return; }
-	l.sp--;
-	const StackEntry16 e = stack[ l.sp ];
-	l.tmin = e.tmin; l.tmax = e.tmax;
-	lane_goto( l, e.node );
-}
-
-/* one trace_seg_tree step (bsp.cc:213-252) */
+/* one trace_seg_tree step (bsp.cc:213-252).  Written as selects over the reference's comparisons:
+ *   near child has work            -> go there over [tmin, u or tmax]; push the far child over [u, tmax] if it has work
+ *   near child is an empty leaf    -> go straight to the far child over [u, tmax] if the segment straddles and it has work
+ *   neither                        -> next pending far side from the stack (the second recursive call, :250-252), or done */
 template< class Map >
 BSPK_HD void lane_node_step( const Map & map, Lane & l, StackEntry16 * stack ) {
 	float nx, ny, nz, d; int32_t c0, c1;
-	map.node( l.node, nx, ny, nz, d, c0, c1 );
+	map.node( l.cur, nx, ny, nz, d, c0, c1 );
 	const float denom = dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );                /* :220 */
 	const float dist = -( dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d );        /* :221 */
 	const float u = dist / denom;                                                  /* :227 */
 	const bool in_range = denom != 0.0f && u >= 0.0f && u <= l.tmax;               /* :226,:232 */
-	const bool flip = in_range && u < l.tmin;                                      /* :235 */
-	const bool both = in_range && !( u < l.tmin );                                 /* :238 */
-	const bool near_child = ( dist > 0.0f ) != flip;                               /* :222,:236 */
-	const int32_t cn = near_child ? c1 : c0;                                       /* children[ near ] */
-	const int32_t cf = near_child ? c0 : c1;                                       /* children[ !near ] */
+	const bool below = u < l.tmin;                                                 /* :235 */
+	const bool both = in_range && !below;                                          /* :238 */
+	const bool near_back = ( dist > 0.0f ) != ( in_range && below );               /* :222,:236 */
+	const int32_t cn = near_back ? c1 : c0;                                        /* children[ near ] */
+	const int32_t cf = near_back ? c0 : c1;                                        /* children[ !near ] */
+	const bool near_ok = cn != kEmptyLeaf;
 	const bool far_work = both && cf != kEmptyLeaf;
-	if( cn != kEmptyLeaf ) {
-		if( far_work ) {                                                           /* far side later, over [u, tmax] (:251) */
-			StackEntry16 e; e.node = cf; e.tmin = u; e.tmax = l.tmax; e.pad = 0;
-			stack[ l.sp ] = e; l.sp++;
-		}
-		if( both ) l.tmax = u;                                                     /* near side over [tmin, u] (:248) */
-		lane_goto( l, cn );
+	const bool do_push = near_ok && far_work;
+	const bool do_pop = !near_ok && !far_work;
+	const bool can_pop = do_pop && l.sp > 0;
+	if( do_push ) {
+		StackEntry16 e; e.node = cf; e.tmin = u; e.tmax = l.tmax; e.pad = 0;
+		stack[ l.sp ] = e;
 	}
-	else if( far_work ) { l.tmin = u; lane_goto( l, cf ); }                        /* near side is an empty leaf: nothing to do there */
-	else lane_pop( l, stack );
-}
-
-/* fetch brush reference l.ri and reset the clip state (bsp.cc:122-125) */
-template< class Map >
-BSPK_HD void lane_load_ref( const Map & map, Lane & l ) {
-	uint32_t first, nraw;
-	map.ref( l.ri, first, nraw, l.brush );
-	l.last_ref = ( nraw & kLastRef ) != 0;
-	l.s = first; l.s_end = first + ( nraw & ~kLastRef );
-	l.b.tfar = l.tmin; l.b.tnear = l.tmax; l.b.far_side = -1; l.b.hit = false; l.b.starts_inside = true;
-	l.need_ref = false;
-}
-
-/* one iteration of trace_seg_brush's side loop (bsp.cc:128-165) as selects; returns false when
- * the brush is rejected (:135).  Flatten guarantees every referenced brush has >= 1 side. */
-BSPK_HD bool lane_side_step( Lane & l, float ex, float ey, float ez, float nx, float ny, float nz, float d ) {
-	const float start_dist = dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d;        /* :131 */
-	const float end_dist = dot3( ex, ey, ez, nx, ny, nz ) - d;                      /* :132 */
-	const float denom = -dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );               /* :141 */
-	const float t = start_dist / denom;                                             /* :142 */
-	const bool rejected = start_dist > 0.0f && end_dist > 0.0f;                     /* :135 */
-	const bool behind = start_dist <= 0.0f && end_dist <= 0.0f;                     /* :137 */
-	const bool crossing = !rejected && !behind;
-	const bool entering = start_dist >= 0.0f;
-	if( crossing && entering ) l.b.starts_inside = false;                           /* :139 */
-	const bool in_range = crossing && t >= l.tmin && t <= l.tmax;                   /* :144 */
-	const bool raise_far = in_range && entering && t >= l.b.tfar;                   /* :147-148 */
-	const bool lower_near = in_range && !entering && t <= l.b.tnear;                /* :154 */
-	if( raise_far ) { l.b.tfar = t; l.b.far_side = ( int32_t ) l.s; }
-	if( lower_near ) l.b.tnear = t;
-	if( raise_far || lower_near ) l.b.hit = true;
-	return !rejected;
+	StackEntry16 top; top.node = kCurDone; top.tmin = l.tmin; top.tmax = l.tmax; top.pad = 0;
+	if( can_pop ) top = stack[ l.sp - 1 ];
+	l.cur = near_ok ? cn : ( far_work ? cf : top.node );
+	l.tmin = near_ok ? l.tmin : ( far_work ? u : top.tmin );
+	l.tmax = near_ok ? ( both ? u : l.tmax ) : top.tmax;                           /* top.tmax == l.tmax unless popped */
+	l.sp += ( do_push ? 1 : 0 ) - ( can_pop ? 1 : 0 );
+	l.s = 0; l.s_end = 0;                                                          /* if this was a leaf: fetch its first brush reference */
 }
 
 /* up to `max_steps` node steps; stops early when the lane leaves node mode */
 template< class Map >
 BSPK_HD void lane_node_phase( const Map & map, Lane & l, StackEntry16 * stack, uint32_t max_steps ) {
-	while( l.mode == kLaneNode && max_steps-- ) lane_node_step( map, l, stack );
+	while( lane_in_node( l ) && max_steps-- ) lane_node_step( map, l, stack );
 }
 
-/* up to `max_steps` side steps, moving through the leaf's brushes */
+/* up to `max_steps` iterations of trace_seg_brush's side loop (bsp.cc:128-165), moving through the
+ * leaf's brushes (trace_seg_leaf, bsp.cc:188-201).  Flatten guarantees every referenced brush has >= 1 side. */
 template< class Map >
 BSPK_HD void lane_leaf_phase( const Map & map, Lane & l, const StackEntry16 * stack, uint32_t max_steps ) {
 	/* end = start + dir * tmax (bsp.cc:121); tmax is the leaf interval's and is constant inside a leaf */
 	float ex = l.r.sx + l.r.dx * l.tmax, ey = l.r.sy + l.r.dy * l.tmax, ez = l.r.sz + l.r.dz * l.tmax;
-	while( l.mode == kLaneLeaf && max_steps-- ) {
-		if( l.need_ref ) lane_load_ref( map, l );
+	while( lane_in_leaf( l ) && max_steps-- ) {
+		if( l.s == l.s_end ) {
+			/* next brush of the leaf: reference ~cur; reset the clip state (bsp.cc:122-125) */
+			uint32_t first, nraw;
+			map.ref( ( uint32_t ) ~l.cur, first, nraw, l.brush );
+			l.s = first; l.s_end = first + ( nraw & ~kLastRef );
+			l.bflags = kBrushInside | ( ( nraw & kLastRef ) ? kBrushLastRef : 0u );
+			l.tfar = l.tmin; l.tnear = l.tmax; l.far_side = -1;
+		}
 		float nx, ny, nz, d;
 		map.side( l.s, nx, ny, nz, d );
-		const bool alive = lane_side_step( l, ex, ey, ez, nx, ny, nz, d );
+		const float start_dist = dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d;    /* :131 */
+		const float end_dist = dot3( ex, ey, ez, nx, ny, nz ) - d;                  /* :132 */
+		const float denom = -dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );           /* :141 */
+		const float t = start_dist / denom;                                         /* :142 */
+		const bool rejected = start_dist > 0.0f && end_dist > 0.0f;                 /* :135 */
+		const bool behind = start_dist <= 0.0f && end_dist <= 0.0f;                 /* :137 */
+		const bool crossing = !rejected && !behind;
+		const bool entering = start_dist >= 0.0f;
+		const bool in_range = crossing && t >= l.tmin && t <= l.tmax;               /* :144 */
+		const bool raise_far = in_range && entering && t >= l.tfar;                 /* :147-148 */
+		const bool lower_near = in_range && !entering && t <= l.tnear;              /* :154 */
+		if( crossing && entering ) l.bflags &= ~kBrushInside;                       /* :139 */
+		if( raise_far ) { l.tfar = t; l.far_side = ( int32_t ) l.s; }
+		if( lower_near ) l.tnear = t;
+		if( raise_far || lower_near ) l.bflags |= kBrushHit;
 		l.s++;
-		if( alive && l.s != l.s_end ) continue;
-		/* brush over (rejected, or side loop complete) */
-		if( alive ) brush_finish( l.b, l.brush, l.h );                              /* bsp.cc:169-182 + :197-200 */
-		if( !l.last_ref ) { l.ri++; l.need_ref = true; continue; }
-		/* leaf over: a hit ends the whole trace (bsp.cc:206), otherwise the next pending far side */
-		if( l.h.hit ) { l.mode = kLaneDone; break; }
-		lane_pop( l, stack );
+		if( !rejected && l.s != l.s_end ) continue;
+
+		/* ---- brush over (rejected, or side loop complete): bsp.cc:169-182 folded into :197-200 */
+		if( !rejected ) {
+			const bool inside = ( l.bflags & kBrushInside ) != 0;
+			if( inside ) l.hflags |= kStartSolidFlag;
+			const bool brush_hit = ( l.bflags & kBrushHit ) && ( inside ? ( l.tnear < l.tfar ) : ( l.tfar <= l.tnear ) );   /* :171,:176 */
+			if( brush_hit ) {
+				const float bt = inside ? l.tnear : l.tfar;
+				if( !( l.hflags & kHitFlag ) || bt < l.ht ) { l.hside = inside ? -1 : l.far_side; l.hbrush = l.brush; }
+				l.hflags |= kHitFlag;                                               /* :198 */
+				if( bt < l.ht ) l.ht = bt;                                          /* :199 */
+			}
+		}
+		l.s = l.s_end;                                                              /* a rejected brush skips its remaining sides */
+		if( !( l.bflags & kBrushLastRef ) ) { l.cur--; continue; }                  /* ~cur + 1: next brush reference of this leaf */
+
+		/* ---- leaf over: a hit ends the whole trace (bsp.cc:206), otherwise the next pending far side */
+		if( l.hflags & kHitFlag ) { l.cur = kCurDone; break; }
+		if( l.sp == 0 ) { l.cur = kCurDone; break; }
+		l.sp--;
+		const StackEntry16 e = stack[ l.sp ];
+		l.cur = e.node; l.tmin = e.tmin; l.tmax = e.tmax;
+		l.s = 0; l.s_end = 0;
 		ex = l.r.sx + l.r.dx * l.tmax; ey = l.r.sy + l.r.dy * l.tmax; ez = l.r.sz + l.r.dz * l.tmax;
 	}
 }
@@ -349,11 +368,12 @@ BSPK_HD void trace_one_phased( const Map & map, float sx, float sy, float sz, fl
 	StackEntry16 stack[ kStack ];
 	Lane l;
 	lane_start( l, sx, sy, sz, ex, ey, ez );
-	while( l.mode != kLaneDone ) {
+	while( !lane_done( l ) ) {
 		lane_node_phase( map, l, stack, node_budget );
 		lane_leaf_phase( map, l, stack, side_budget );
 	}
-	r_out = l.r; h_out = l.h;
+	r_out = l.r;
+	lane_hit_state( l, h_out );
 }
 
 /* BSP::position_to_leaf (bsp.cc:273-286) on the flattened nodes; returns the file's leaf index */

@@ -136,17 +136,22 @@ struct SmemAllMap {
 	}
 };
 
+/* one 256-bit read-only load (sm_100: LDG.E.ENL2.256.CONSTANT) fetches a whole 32-byte NodeRec --
+ * plane and children in ONE L1 request instead of two (the city10k profile showed the L1 data pipe
+ * at 75 % with two scattered requests per node step) */
+__device__ __forceinline__ void ldg256( const void * p, float & a, float & b, float & c, float & d, int32_t & e, int32_t & f, int32_t & g, int32_t & h ) {
+	asm volatile( "ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"( a ), "=f"( b ), "=f"( c ), "=f"( d ), "=r"( e ), "=r"( f ), "=r"( g ), "=r"( h ) : "l"( p ) );
+}
+
 struct GlobalMap {
 	const NodeRec * nodes; const BrushRef * refs; const SideRec * sides;   /* global memory, read-only path */
 	__device__ __forceinline__ void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const {
-		const float4 p = __ldg( reinterpret_cast< const float4 * >( &nodes[ i ] ) );
-		const int2 c = __ldg( reinterpret_cast< const int2 * >( &nodes[ i ].child[ 0 ] ) );
-		nx = p.x; ny = p.y; nz = p.z; d = p.w; c0 = c.x; c1 = c.y;
+		int32_t o0, o1;
+		ldg256( &nodes[ i ], nx, ny, nz, d, c0, c1, o0, o1 );
 	}
 	__device__ __forceinline__ void node_full( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1, int32_t & o0, int32_t & o1 ) const {
-		const float4 p = __ldg( reinterpret_cast< const float4 * >( &nodes[ i ] ) );
-		const int4 c = __ldg( reinterpret_cast< const int4 * >( &nodes[ i ].child[ 0 ] ) );
-		nx = p.x; ny = p.y; nz = p.z; d = p.w; c0 = c.x; c1 = c.y; o0 = c.z; o1 = c.w;
+		ldg256( &nodes[ i ], nx, ny, nz, d, c0, c1, o0, o1 );
 	}
 	__device__ __forceinline__ void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const {
 		const uint4 r = __ldg( reinterpret_cast< const uint4 * >( &refs[ i ] ) );
@@ -339,8 +344,8 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TracePa
  * a leaf phase when at least `leaf_threshold` lanes wait in a leaf (or nobody can step nodes),
  * otherwise a node phase.  Lanes of the other kind just keep their registers.  Finished lanes
  * are re-filled as before. */
-template< int kMode, int kStack, int kMaxThreads >
-__global__ void __launch_bounds__( kMaxThreads ) trace_phased( const TraceParams p ) {
+template< int kMode, int kStack, int kMaxThreads, int kMinBlocks >
+__global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const TraceParams p ) {
 	extern __shared__ __align__( 128 ) unsigned char smem[];
 	__shared__ __align__( 8 ) uint64_t stage_bar;
 
@@ -388,18 +393,15 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_phased( const TraceParams
 	bool more_work = true;
 
 	Lane l;
-	l.mode = kLaneIdle;
-	l.r.sx = l.r.sy = l.r.sz = l.r.dx = l.r.dy = l.r.dz = 0.0f;
-	l.tmin = 0.0f; l.tmax = 1.0f; l.node = 0; l.sp = 0;
-	hit_init( l.h );
-	l.ri = l.s = l.s_end = 0; l.brush = -1; l.last_ref = false; l.need_ref = false;
-	l.b.tfar = l.b.tnear = 0.0f; l.b.far_side = -1; l.b.hit = false; l.b.starts_inside = true;
+	lane_start( l, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f );
+	l.cur = kCurIdle;
+	l.brush = -1; l.bflags = 0; l.tfar = l.tnear = 0.0f; l.far_side = -1;
 	StackEntry16 stack[ kStack ];
 	uint32_t seg = 0, my_hits = 0;
 
 	for( ;; ) {
 		/* ---- warp-level work fetch + compaction */
-		const unsigned idle = __ballot_sync( kFull, l.mode == kLaneIdle );
+		const unsigned idle = __ballot_sync( kFull, lane_idle( l ) );
 		const unsigned n_idle = __popc( idle );
 		if( more_work && n_idle >= p.refill ) {
 			if( blk_next == blk_end ) {
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_phased( const TraceParams
 			if( more_work ) {
 				const uint32_t avail = blk_end - blk_next;
 				const uint32_t rank = __popc( idle & lt_mask );
-				if( l.mode == kLaneIdle && rank < avail ) {
+				if( lane_idle( l ) && rank < avail ) {
 					seg = blk_next + rank;
 					if( p.segs24 ) {
 						const float2 * sp24 = p.segs24 + ( size_t ) seg * 3;
@@ -433,30 +435,28 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_phased( const TraceParams
 		}
 
 		/* ---- pick the phase most lanes are waiting for */
-		const unsigned in_node = __ballot_sync( kFull, l.mode == kLaneNode );
-		const unsigned in_leaf = __ballot_sync( kFull, l.mode == kLaneLeaf );
+		const unsigned in_node = __ballot_sync( kFull, lane_in_node( l ) );
+		const unsigned in_leaf = __ballot_sync( kFull, lane_in_leaf( l ) );
 		if( ( in_node | in_leaf ) == 0u ) {
 			if( !more_work ) break;
 			continue;
 		}
-		if( in_node == 0u || ( uint32_t ) __popc( in_leaf ) >= p.leaf_threshold ) {
-			if( l.mode == kLaneLeaf ) lane_leaf_phase( map, l, stack, p.side_steps );
-		}
-		else {
-			if( l.mode == kLaneNode ) lane_node_phase( map, l, stack, p.max_steps );
-		}
+		if( in_node == 0u || ( uint32_t ) __popc( in_leaf ) >= p.leaf_threshold ) lane_leaf_phase( map, l, stack, p.side_steps );
+		else lane_node_phase( map, l, stack, p.max_steps );
 
 		/* ---- retire finished segments */
-		if( l.mode == kLaneDone ) {
-			const ResultRec o = make_result( l.h, side_plane );
+		if( lane_done( l ) ) {
+			HitState h;
+			lane_hit_state( l, h );
+			const ResultRec o = make_result( h, side_plane );
 			if( p.out ) st_stream4( p.out + seg, o.t, __int_as_float( o.plane ), __int_as_float( o.brush ), __uint_as_float( o.flags ) );
 			if( p.pos ) {
 				float px, py, pz;
-				make_pos( l.r, l.h, px, py, pz );                               /* bsp.cc:265-267 */
-				st_stream4( p.pos + seg, px, py, pz, l.h.t );
+				make_pos( l.r, h, px, py, pz );                                 /* bsp.cc:265-267 */
+				st_stream4( p.pos + seg, px, py, pz, h.t );
 			}
-			my_hits += ( uint32_t ) l.h.hit;
-			l.mode = kLaneIdle;
+			my_hits += ( uint32_t ) h.hit;
+			l.cur = kCurIdle;
 		}
 	}
 
