@@ -118,6 +118,13 @@ __device__ __forceinline__ uint4 lds128u( uint32_t addr ) {
 	return v;
 }
 
+/* keep a computed shared-window address in a register: without this the compiler re-derives it from
+ * the CTA's shared window (S2UR SR_CgaCtaId + 3 uniform ops) at every load site inside the hot loops */
+__device__ __forceinline__ uint32_t opaque_u32( uint32_t v ) {
+	asm volatile( "" : "+r"( v ) );
+	return v;
+}
+
 struct SmemAllMap {
 	uint32_t nodes, refs, sides;   /* shared-window byte addresses of the three sections */
 	__device__ __forceinline__ void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const {
@@ -216,12 +223,12 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TracePa
 	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
 	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
 	if constexpr( kMode == kSmemAll ) {
-		map.nodes = smem_u32( smem );
-		map.refs = map.nodes + ( uint32_t ) p.off_refs;
-		map.sides = map.nodes + ( uint32_t ) p.off_sides;
+		map.nodes = opaque_u32( smem_u32( smem ) );
+		map.refs = opaque_u32( map.nodes + ( uint32_t ) p.off_refs );
+		map.sides = opaque_u32( map.nodes + ( uint32_t ) p.off_sides );
 	}
 	else if constexpr( kMode == kSmemTop ) {
-		map.top = smem_u32( smem );
+		map.top = opaque_u32( smem_u32( smem ) );
 		map.top_nodes = p.top_nodes;
 		map.g.nodes = g_nodes; map.g.refs = g_refs; map.g.sides = g_sides;
 	}
@@ -371,12 +378,12 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
 	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
 	if constexpr( kMode == kSmemAll ) {
-		map.nodes = smem_u32( smem );
-		map.refs = map.nodes + ( uint32_t ) p.off_refs;
-		map.sides = map.nodes + ( uint32_t ) p.off_sides;
+		map.nodes = opaque_u32( smem_u32( smem ) );
+		map.refs = opaque_u32( map.nodes + ( uint32_t ) p.off_refs );
+		map.sides = opaque_u32( map.nodes + ( uint32_t ) p.off_sides );
 	}
 	else if constexpr( kMode == kSmemTop ) {
-		map.top = smem_u32( smem );
+		map.top = opaque_u32( smem_u32( smem ) );
 		map.top_nodes = p.top_nodes;
 		map.g.nodes = g_nodes; map.g.refs = g_refs; map.g.sides = g_sides;
 	}

@@ -30,6 +30,20 @@ def test_maps_are_deterministic():
     assert ibsp.to_bytes(mapgen.rooms8(seed=2)) != a
 
 
+def test_c_and_numpy_tree_builders_agree():
+    """tools/bspc.c is the numpy split search transcribed; both must emit the same bytes."""
+    import functools
+    from tools import ibsp, mapgen
+    fast = mapgen.rooms8()
+    orig = mapgen.compile_bsp
+    mapgen.compile_bsp = functools.partial(orig, builder="numpy")
+    try:
+        slow = mapgen.rooms8()
+    finally:
+        mapgen.compile_bsp = orig
+    assert ibsp.to_bytes(fast) == ibsp.to_bytes(slow)
+
+
 @pytest.mark.parametrize("name,lo_brushes,hi_brushes", [("rooms8", 400, 600), ("city10k", 9000, 11500)])
 def test_compiled_tree_invariants(maps, name, lo_brushes, hi_brushes):
     m, _ = maps(name)

@@ -166,24 +166,9 @@ def _textures_array(textures) -> np.ndarray:
     return arr
 
 
-def compile_bsp(bl: BrushList, world_min, world_max, textures=None, leaf_max: int = 6,
-                cost_traverse: float = 1.0, cost_brush: float = 2.0, max_depth: int = 56,
-                empty_bonus: float = 0.8) -> ibsp.IBSP:
-    """Axial kd-style BSP over the brush AABBs with a surface-area heuristic.
-
-    Every leaf lists *every* brush whose AABB overlaps the leaf cell with positive
-    volume (over-inclusion is harmless: the reference clips the segment against
-    the brush itself, bsp.cc:120-183).  Nodes are emitted in depth-first order,
-    node 0 is the root (the reference starts at node 0, bsp.cc:263).
-    """
-    textures = textures or DEFAULT_TEXTURES
-    nb = len(bl)
-    bmin = np.asarray(bl.bmin, np.float64).reshape(nb, 3)
-    bmax = np.asarray(bl.bmax, np.float64).reshape(nb, 3)
-    lo0 = np.asarray(world_min, np.float64)
-    hi0 = np.asarray(world_max, np.float64)
-
-    nodes: list[list] = []       # [plane_idx, child0, child1, lo, hi]
+def _tree_numpy(bmin, bmax, lo0, hi0, leaf_max, cost_traverse, cost_brush, max_depth, empty_bonus):
+    """reference implementation of the SAH split search (slow: ~150 us of numpy overhead per node)."""
+    nodes: list[list] = []       # [axis, c, child0, child1, lo, hi]
     leaves: list[tuple] = []     # (ids, lo, hi)
     stats = {"max_depth": 0, "forced_leaves": 0}
 
@@ -216,14 +201,11 @@ def compile_bsp(bl: BrushList, world_min, world_max, textures=None, leaf_max: in
                 best = (float(cost[i]), a, float(cand[i]), int(n_back[i]), int(n_front[i]))
         return best
 
-    # explicit stack; children patched into the parent slot when known
     root_ids = np.nonzero(np.all(bmax > lo0, axis=1) & np.all(bmin < hi0, axis=1))[0]
     work = [(root_ids, lo0, hi0, 0, -1, 0)]  # ids, lo, hi, depth, parent, slot
-    root_ref = None
     while work:
         ids, lo, hi, depth, parent, slot = work.pop()
         n = len(ids)
-        ref = None
         if n == 0 or depth >= max_depth:
             if n:
                 stats["forced_leaves"] += 1
@@ -235,41 +217,138 @@ def compile_bsp(bl: BrushList, world_min, world_max, textures=None, leaf_max: in
             if axis < 0 or (cost >= leaf_cost and n <= leaf_max) or (n > leaf_max and not progress and cost >= leaf_cost):
                 ref = make_leaf(ids, lo, hi, depth)
             else:
-                normal = [0.0, 0.0, 0.0]
-                normal[axis] = 1.0
-                pidx = bl.plane(normal[0], normal[1], normal[2], c)
                 ref = len(nodes)
-                nodes.append([pidx, 0, 0, lo, hi])
+                nodes.append([axis, c, 0, 0, lo, hi])
                 hi_back = hi.copy(); hi_back[axis] = c
                 lo_front = lo.copy(); lo_front[axis] = c
-                back_ids = ids[bmin[ids, axis] < c]
-                front_ids = ids[bmax[ids, axis] > c]
                 # push back first so the front child is compiled first (DFS preorder, front first)
-                work.append((back_ids, lo, hi_back, depth + 1, ref, 1))
-                work.append((front_ids, lo_front, hi, depth + 1, ref, 0))
-        if parent < 0:
-            root_ref = ref
-        else:
-            nodes[parent][1 + slot] = ref
+                work.append((ids[bmin[ids, axis] < c], lo, hi_back, depth + 1, ref, 1))
+                work.append((ids[bmax[ids, axis] > c], lo_front, hi, depth + 1, ref, 0))
+        if parent >= 0:
+            nodes[parent][2 + slot] = ref
+    nn, nl = len(nodes), len(leaves)
+    out = {
+        "axis": np.array([n[0] for n in nodes], np.int32), "c": np.array([n[1] for n in nodes], np.float64),
+        "children": np.array([[n[2], n[3]] for n in nodes], np.int32).reshape(nn, 2),
+        "node_lo": np.array([n[4] for n in nodes], np.float64).reshape(nn, 3), "node_hi": np.array([n[5] for n in nodes], np.float64).reshape(nn, 3),
+        "leaf_count": np.array([len(l[0]) for l in leaves], np.int64),
+        "leaf_lo": np.array([l[1] for l in leaves], np.float64).reshape(nl, 3), "leaf_hi": np.array([l[2] for l in leaves], np.float64).reshape(nl, 3),
+        "leaf_ids": np.concatenate([l[0] for l in leaves]).astype(np.int32) if leaves else np.zeros(0, np.int32),
+    }
+    out["leaf_first"] = np.concatenate(([0], np.cumsum(out["leaf_count"])[:-1])).astype(np.int64) if nl else np.zeros(0, np.int64)
+    return out, stats
 
-    if root_ref is not None and root_ref < 0:
-        # the reference always starts at node 0 (bsp.cc:263): wrap a lone leaf in a node
-        pidx = bl.plane(1.0, 0.0, 0.0, float(lo0[0]))
-        leaves.append((np.zeros(0, np.int64), lo0, hi0))
-        nodes.append([pidx, root_ref, -len(leaves), lo0, hi0])
 
-    # ---- lumps
-    node_arr = np.zeros(len(nodes), ibsp.NODE_DT)
-    for i, (pidx, c0, c1, lo, hi) in enumerate(nodes):
-        node_arr[i] = (pidx, (c0, c1), tuple(np.floor(lo).astype(np.int64)), tuple(np.ceil(hi).astype(np.int64)))
-    leaf_arr = np.zeros(len(leaves), ibsp.LEAF_DT)
-    lb_chunks = []
-    off = 0
-    for i, (ids, lo, hi) in enumerate(leaves):
-        leaf_arr[i] = (0, 0, tuple(np.floor(lo).astype(np.int64)), tuple(np.ceil(hi).astype(np.int64)), 0, 0, off, len(ids))
-        lb_chunks.append(ids.astype(np.uint32))
-        off += len(ids)
-    leaf_brushes = np.concatenate(lb_chunks) if lb_chunks else np.zeros(0, np.uint32)
+_bspc = None
+
+
+def _load_bspc():
+    """tools/bspc.c built on first use (gcc -O2 -ffp-contract=off); None if no compiler is available."""
+    global _bspc
+    if _bspc is not None:
+        return _bspc or None
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src, so = os.path.join(here, "bspc.c"), os.path.join(here, "libbspc.so")
+    try:
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            tmp = so + ".tmp%d" % os.getpid()
+            subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", tmp, src], check=True)
+            os.replace(tmp, so)
+        lib = C.CDLL(so)
+        dp = C.POINTER(C.c_double)
+        lib.bspc_build.restype = C.c_void_p
+        lib.bspc_build.argtypes = [C.c_int64, dp, dp, dp, dp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double]
+        lib.bspc_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        lib.bspc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.bspc_free.argtypes = [C.c_void_p]
+        _bspc = lib
+    except Exception:
+        _bspc = False
+    return _bspc or None
+
+
+def _tree_c(lib, bmin, bmax, lo0, hi0, leaf_max, cost_traverse, cost_brush, max_depth, empty_bonus):
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    bmin = np.ascontiguousarray(bmin, np.float64); bmax = np.ascontiguousarray(bmax, np.float64)
+    lo0 = np.ascontiguousarray(lo0, np.float64); hi0 = np.ascontiguousarray(hi0, np.float64)
+    t = lib.bspc_build(len(bmin), bmin.ctypes.data_as(dp), bmax.ctypes.data_as(dp), lo0.ctypes.data_as(dp), hi0.ctypes.data_as(dp),
+                       leaf_max, cost_traverse, cost_brush, max_depth, empty_bonus)
+    cnt = (C.c_int64 * 5)()
+    lib.bspc_counts(t, cnt)
+    nn, nl, ni = int(cnt[0]), int(cnt[1]), int(cnt[2])
+    node_i = np.zeros((nn, 3), np.int32); node_f = np.zeros((nn, 7), np.float64)
+    leaf_i = np.zeros((nl, 2), np.int64); leaf_f = np.zeros((nl, 6), np.float64); ids = np.zeros(ni, np.int32)
+    lib.bspc_export(t, node_i.ctypes.data, node_f.ctypes.data, leaf_i.ctypes.data, leaf_f.ctypes.data, ids.ctypes.data)
+    lib.bspc_free(t)
+    out = {"axis": node_i[:, 0].copy(), "c": node_f[:, 0].copy(), "children": node_i[:, 1:3].copy(),
+           "node_lo": node_f[:, 1:4].copy(), "node_hi": node_f[:, 4:7].copy(),
+           "leaf_first": leaf_i[:, 0].copy(), "leaf_count": leaf_i[:, 1].copy(),
+           "leaf_lo": leaf_f[:, 0:3].copy(), "leaf_hi": leaf_f[:, 3:6].copy(), "leaf_ids": ids}
+    return out, {"max_depth": int(cnt[3]), "forced_leaves": int(cnt[4])}
+
+
+def compile_bsp(bl: BrushList, world_min, world_max, textures=None, leaf_max: int = 6,
+                cost_traverse: float = 1.0, cost_brush: float = 2.0, max_depth: int = 56,
+                empty_bonus: float = 0.8, builder: str = "auto") -> ibsp.IBSP:
+    """Axial kd-style BSP over the brush AABBs with a surface-area heuristic.
+
+    Every leaf lists *every* brush whose AABB overlaps the leaf cell with positive
+    volume (over-inclusion is harmless: the reference clips the segment against
+    the brush itself, bsp.cc:120-183).  Nodes are emitted in depth-first order,
+    node 0 is the root (the reference starts at node 0, bsp.cc:263).
+    ``builder``: "c" (tools/bspc.c), "numpy" (the slow reference implementation), or "auto";
+    both produce the same bytes (tests/test_tools.py).
+    """
+    textures = textures or DEFAULT_TEXTURES
+    nb = len(bl)
+    bmin = np.asarray(bl.bmin, np.float64).reshape(nb, 3)
+    bmax = np.asarray(bl.bmax, np.float64).reshape(nb, 3)
+    lo0 = np.asarray(world_min, np.float64)
+    hi0 = np.asarray(world_max, np.float64)
+    lib = _load_bspc() if builder in ("auto", "c") else None
+    if builder == "c" and lib is None:
+        raise RuntimeError("tools/bspc.c could not be built")
+    if lib is not None:
+        tree, stats = _tree_c(lib, bmin, bmax, lo0, hi0, leaf_max, cost_traverse, cost_brush, max_depth, empty_bonus)
+    else:
+        tree, stats = _tree_numpy(bmin, bmax, lo0, hi0, leaf_max, cost_traverse, cost_brush, max_depth, empty_bonus)
+
+    nn, nl = len(tree["axis"]), len(tree["leaf_count"])
+    # split planes join the planes lump in node order (de-duplicated against the brush planes)
+    node_plane = np.zeros(nn, np.uint32)
+    for i in range(nn):
+        normal = [0.0, 0.0, 0.0]
+        normal[int(tree["axis"][i])] = 1.0
+        node_plane[i] = bl.plane(normal[0], normal[1], normal[2], float(tree["c"][i]))
+    children = tree["children"]
+    leaf_first, leaf_count = tree["leaf_first"], tree["leaf_count"]
+    leaf_lo, leaf_hi = tree["leaf_lo"], tree["leaf_hi"]
+    node_lo, node_hi = tree["node_lo"], tree["node_hi"]
+    if nn == 0:
+        # the reference always starts at node 0 (bsp.cc:263): wrap the lone leaf in a node
+        node_plane = np.array([bl.plane(1.0, 0.0, 0.0, float(lo0[0]))], np.uint32)
+        children = np.array([[-1, -(nl + 1)]], np.int32)
+        node_lo, node_hi = lo0[None, :], hi0[None, :]
+        leaf_first = np.concatenate((leaf_first, [int(leaf_count.sum())])).astype(np.int64)
+        leaf_count = np.concatenate((leaf_count, [0])).astype(np.int64)
+        leaf_lo = np.vstack((leaf_lo, lo0[None, :])); leaf_hi = np.vstack((leaf_hi, hi0[None, :]))
+        nn, nl = 1, nl + 1
+
+    node_arr = np.zeros(nn, ibsp.NODE_DT)
+    node_arr["plane"] = node_plane
+    node_arr["children"] = children
+    node_arr["mins"] = np.floor(node_lo).astype(np.int32)
+    node_arr["maxs"] = np.ceil(node_hi).astype(np.int32)
+    leaf_arr = np.zeros(nl, ibsp.LEAF_DT)
+    leaf_arr["mins"] = np.floor(leaf_lo).astype(np.int32)
+    leaf_arr["maxs"] = np.ceil(leaf_hi).astype(np.int32)
+    leaf_arr["first_brush"] = leaf_first.astype(np.uint32)
+    leaf_arr["num_brushes"] = leaf_count.astype(np.uint32)
+    leaf_brushes = tree["leaf_ids"].astype(np.uint32)
+    off = int(leaf_count.sum())
 
     plane_arr = np.zeros(len(bl.planes), ibsp.PLANE_DT)
     if bl.planes:
@@ -286,7 +365,7 @@ def compile_bsp(bl: BrushList, world_min, world_max, textures=None, leaf_max: in
 
     meta = dict(stats)
     meta.update(world_min=[float(v) for v in lo0], world_max=[float(v) for v in hi0],
-                leaf_brush_refs=int(off), avg_leaf_brushes=float(off) / max(1, len(leaves)))
+                leaf_brush_refs=int(off), avg_leaf_brushes=float(off) / max(1, nl))
     return ibsp.IBSP(_textures_array(textures), plane_arr, node_arr, leaf_arr, leaf_brushes, brush_arr, side_arr, meta)
 
 
@@ -512,7 +591,7 @@ def cache_dir() -> str:
 
 def _source_digest() -> str:
     h = hashlib.sha256()
-    for fn in (__file__, ibsp.__file__):
+    for fn in (__file__, ibsp.__file__, os.path.join(os.path.dirname(os.path.abspath(__file__)), "bspc.c")):
         with open(fn, "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:12]
