@@ -253,3 +253,38 @@ def test_odd_map_on_gpu(native, oracle_mod):
         res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
         _compare(res, pos, exp, exp_pos, f"odd map variant {variant}")
     g.close()
+
+
+@pytest.mark.parametrize("variant", ["toptree", "global"])
+def test_parity_mega200k_short_moves(native, maps, oracle_mod, variant):
+    """C5: ~200k-brush map (54 MB flattened image, L2-resident), short player-movement segments."""
+    from tools import mapgen, seggen
+    m, _ = maps("mega200k")
+    lo, hi = mapgen.seg_bounds(m)
+    segs = np.vstack((seggen.edge_cases(m, 8192, 9), seggen.long_rays(5, 0, 400_000, lo, hi, 1.0, 32.0),
+                      seggen.uniform(6, 0, 50_000, lo, hi)))
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    assert g.info()["map_bytes"] > 40 * 1024 * 1024 and g.info()["tree_depth"] <= 32
+    g.set_option(1, VARIANTS[variant])
+    pos = np.zeros((len(segs), 4), np.float32)
+    res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+    _compare(res, pos, exp, exp_pos, f"mega200k/{variant}")
+    g.close()
+
+
+def test_parity_camera_grid(native, maps, oracle_mod):
+    """C4: coherent pinhole-grid segments (row-major) and the same segments shuffled."""
+    from tools import mapgen, seggen
+    m, _ = maps("city10k")
+    lo, hi = mapgen.seg_bounds(m)
+    views = seggen.make_views(4, 3, lo, hi)
+    segs = seggen.camera(views, 480, 270, 0, 3 * 480 * 270)
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    res = g.trace(segs)
+    _compare(res, None, exp, exp_pos, "camera grid")
+    perm = np.random.Generator(np.random.PCG64(1)).permutation(len(segs))
+    res_s = g.trace(np.ascontiguousarray(segs[perm]))
+    _compare(res_s, None, exp[perm], None, "camera grid shuffled")
+    g.close()
