@@ -288,3 +288,19 @@ def test_parity_camera_grid(native, maps, oracle_mod):
     res_s = g.trace(np.ascontiguousarray(segs[perm]))
     _compare(res_s, None, exp[perm], None, "camera grid shuffled")
     g.close()
+
+
+def test_depth_frame_demo(native, maps, oracle_mod):
+    """tools/render_depth.py: a camera frame through one batched call (caller integration, 8f N2)."""
+    from tools import mapgen, render_depth, seggen
+    m, path = maps("city10k")
+    lo, hi = mapgen.seg_bounds(m)
+    views = seggen.make_views(4, 2, lo, hi)
+    g = native.BspGpu(path)
+    w, h = 160, 90
+    for device in (True, False):
+        t, hit = render_depth.render(g, views, w, h, view=1, device=device)
+        exp, _, _ = oracle_mod.Port(m).trace(seggen.camera(views, w, h, w * h, w * h))
+        assert np.array_equal(bits(t.reshape(-1)), bits(exp["t"]))
+        assert np.array_equal(hit.reshape(-1), (exp["flags"] & 1).astype(bool))
+    g.close()
