@@ -11,6 +11,7 @@
 
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,7 @@ TraceKernel pick_kernel( int mode, int depth, int threads, int sched ) {
 } // namespace
 
 struct bspgpu {
+	std::mutex lock;              /* calls on one handle are serialised (host state + the handle's stream) */
 	int device = 0;
 	int sm_count = 0;
 	int max_smem_optin = 0;
@@ -84,6 +86,7 @@ struct bspgpu {
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 96 * 1024;
 	int64_t opt_chunk = 2ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;   /* 0 = per-variant default */
 	int64_t opt_sched = 0, opt_side_steps = 8, opt_leaf_threshold = 16;
+	uint64_t opt_max_launch = kMaxLaunchSegs;   /* segments per kernel launch (lowered by tests to exercise the multi-launch path) */
 
 	/* launch configuration, recomputed only after an option changed */
 	bool cfg_valid = false;
@@ -164,8 +167,8 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 
 	h->last_variant = ( uint32_t ) variant; h->last_threads = ( uint32_t ) threads; h->last_grid = ( uint32_t ) grid; h->last_smem = smem;
 
-	for( uint64_t done = 0; done < n; done += kMaxLaunchSegs ) {
-		const uint64_t cnt = n - done < kMaxLaunchSegs ? n - done : kMaxLaunchSegs;
+	for( uint64_t done = 0; done < n; done += h->opt_max_launch ) {
+		const uint64_t cnt = n - done < h->opt_max_launch ? n - done : h->opt_max_launch;
 		unsigned long long * next = h->d_counters + 1 + ( h->launch_seq++ % kCounterSlots );
 		CK( cudaMemsetAsync( next, 0, sizeof( unsigned long long ), st ) );
 		p.segs = packed24 ? nullptr : reinterpret_cast< const float4 * >( d_segs ) + done * 2;
@@ -305,6 +308,7 @@ void bspgpu_destroy( bspgpu_t * h ) {
 
 int bspgpu_trace_pos( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result * out, bspgpu_pos * pos, unsigned flags ) {
 	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: null handle" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	if( n && ( !segs || ( !out && !pos ) ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: null segs, or both out and pos null" );
 	const bool segs_dev = ( flags & BSPGPU_SEGS_DEVICE ) != 0, out_dev = ( flags & BSPGPU_OUT_DEVICE ) != 0;
 	const bool packed = ( flags & BSPGPU_SEGS_PACKED24 ) != 0;
@@ -379,6 +383,7 @@ int bspgpu_trace( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result * o
 
 int bspgpu_hit_count( bspgpu_t * h, uint64_t * hits ) {
 	if( !h || !hits ) return fail( BSPGPU_E_INVALID, "bspgpu_hit_count: null argument" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	CK( cudaSetDevice( h->device ) );
 	unsigned long long v = 0;
 	CK( cudaMemcpyAsync( &v, h->d_counters, sizeof( v ), cudaMemcpyDeviceToHost, h->stream() ) );
@@ -389,6 +394,7 @@ int bspgpu_hit_count( bspgpu_t * h, uint64_t * hits ) {
 
 int bspgpu_hit_count_device( bspgpu_t * h, void * dev_u64 ) {
 	if( !h || !dev_u64 ) return fail( BSPGPU_E_INVALID, "bspgpu_hit_count_device: null argument" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	CK( cudaSetDevice( h->device ) );
 	CK( cudaMemcpyAsync( dev_u64, h->d_counters, sizeof( unsigned long long ), cudaMemcpyDeviceToDevice, h->stream() ) );
 	return BSPGPU_OK;
@@ -396,6 +402,7 @@ int bspgpu_hit_count_device( bspgpu_t * h, void * dev_u64 ) {
 
 int bspgpu_leaf( bspgpu_t * h, const float * pts, uint32_t stride, uint64_t n, int32_t * leaf, unsigned flags ) {
 	if( !h || ( n && ( !pts || !leaf ) ) || stride < 3 ) return fail( BSPGPU_E_INVALID, "bspgpu_leaf: bad argument" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	if( n == 0 ) return BSPGPU_OK;
 	CK( cudaSetDevice( h->device ) );
 	cudaStream_t st = h->stream();
@@ -420,6 +427,7 @@ int bspgpu_leaf( bspgpu_t * h, const float * pts, uint32_t stride, uint64_t n, i
 
 int bspgpu_generate( bspgpu_t * h, const bspgpu_gen_desc * g, uint64_t first, uint64_t count, void * dev_segs ) {
 	if( !h || !g || ( count && !dev_segs ) ) return fail( BSPGPU_E_INVALID, "bspgpu_generate: null argument" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	if( g->kind > 2 ) return fail( BSPGPU_E_INVALID, "bspgpu_generate: unknown kind" );
 	if( count == 0 ) return BSPGPU_OK;
 	CK( cudaSetDevice( h->device ) );
@@ -454,6 +462,7 @@ int bspgpu_generate( bspgpu_t * h, const bspgpu_gen_desc * g, uint64_t first, ui
 
 int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_set_option: null handle" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	h->cfg_valid = false;
 	switch( option ) {
 		case BSPGPU_OPT_VARIANT: if( value < 0 || value > 3 ) return fail( BSPGPU_E_INVALID, "bad variant" ); h->opt_variant = value; break;
@@ -467,6 +476,9 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 		case BSPGPU_OPT_SCHEDULER: h->opt_sched = value; break;
 		case BSPGPU_OPT_SIDE_STEPS: h->opt_side_steps = value; break;
 		case BSPGPU_OPT_LEAF_THRESHOLD: h->opt_leaf_threshold = value; break;
+		case BSPGPU_OPT_MAX_LAUNCH_SEGMENTS:
+			if( value < 32 || ( uint64_t ) value > kMaxLaunchSegs ) return fail( BSPGPU_E_INVALID, "max launch segments must be in [32, 2^30]" );
+			h->opt_max_launch = ( uint64_t ) value; break;
 		default: return fail( BSPGPU_E_INVALID, "bspgpu_set_option: unknown option" );
 	}
 	return BSPGPU_OK;
@@ -474,6 +486,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 
 int bspgpu_set_stream( bspgpu_t * h, void * cuda_stream ) {
 	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_set_stream: null handle" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	h->user_stream = ( cudaStream_t ) cuda_stream;
 	h->use_user_stream = true;
 	return BSPGPU_OK;
@@ -481,6 +494,7 @@ int bspgpu_set_stream( bspgpu_t * h, void * cuda_stream ) {
 
 int bspgpu_reset_stream( bspgpu_t * h ) {
 	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_reset_stream: null handle" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	h->user_stream = nullptr;
 	h->use_user_stream = false;
 	return BSPGPU_OK;
@@ -488,6 +502,7 @@ int bspgpu_reset_stream( bspgpu_t * h ) {
 
 int bspgpu_sync( bspgpu_t * h ) {
 	if( !h ) return fail( BSPGPU_E_INVALID, "bspgpu_sync: null handle" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	CK( cudaSetDevice( h->device ) );
 	CK( cudaStreamSynchronize( h->stream() ) );
 	return BSPGPU_OK;
@@ -495,6 +510,7 @@ int bspgpu_sync( bspgpu_t * h ) {
 
 int bspgpu_get_info( bspgpu_t * h, bspgpu_info * info ) {
 	if( !h || !info ) return fail( BSPGPU_E_INVALID, "bspgpu_get_info: null argument" );
+	std::lock_guard< std::mutex > guard( h->lock );
 	memset( info, 0, sizeof( *info ) );
 	info->abi_version = BSPGPU_ABI_VERSION;
 	info->device = h->device; info->sm_count = ( uint32_t ) h->sm_count;

@@ -8,8 +8,8 @@
  * replaces or extends.  Plain pointers and sizes only -- no CUDA, torch or C++
  * types cross this boundary.
  *
- * Threading: calls on one handle are serialised on the handle's stream and, unless
- * BSPGPU_ASYNC is passed, synchronous on return.  Different handles are independent.
+ * Threading: calls on one handle are serialised (a per-handle mutex + the handle's stream) and,
+ * unless BSPGPU_ASYNC is passed, synchronous on return.  Different handles are independent.
  * Errors: every int-returning call gives 0 on success or a negative BSPGPU_E_* code;
  * bspgpu_last_error() then returns a thread-local message.  There is no CPU fallback:
  * without a usable sm_100 device every compute call fails with BSPGPU_E_CUDA.
@@ -108,7 +108,8 @@ enum {
 	BSPGPU_OPT_BLOCK_SEGS = 8,      /* consecutive segments a warp claims per global atomic (multiple of 32) */
 	BSPGPU_OPT_SCHEDULER = 9,       /* 0 = phase-scheduled lanes (default), 1 = round-based while-while kernel */
 	BSPGPU_OPT_SIDE_STEPS = 10,     /* brush-side steps a lane takes per leaf phase */
-	BSPGPU_OPT_LEAF_THRESHOLD = 11  /* lanes waiting in a leaf that make a warp run a leaf phase (1..32) */
+	BSPGPU_OPT_LEAF_THRESHOLD = 11, /* lanes waiting in a leaf that make a warp run a leaf phase (1..32) */
+	BSPGPU_OPT_MAX_LAUNCH_SEGMENTS = 12 /* segments per kernel launch, default and maximum 2^30 (in-kernel indices are 32-bit) */
 };
 
 typedef struct bspgpu_info {

@@ -200,6 +200,30 @@ def test_full_size_properties(native, maps, oracle_mod):
     g.close()
 
 
+def test_multi_launch_and_concurrent_callers(native, maps, oracle_mod):
+    """n larger than one launch's segment cap is split into several launches; calls from several
+    host threads on one handle are serialised by the handle's mutex."""
+    import threading
+    m, _ = maps("rooms8")
+    segs = _segments(m, 150_000, 50_000, 20_000, 4096)
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    g.set_option(12, 40_000)                       # ~6 launches per call
+    res = g.trace(segs)
+    _compare(res, None, exp, exp_pos, "multi-launch")
+    assert g.info()["last_launches"] == -(-len(segs) // 40_000)
+    assert g.hit_count() == int((exp["flags"] & 1).sum())
+    outs = [None] * 4
+
+    def work(i):
+        outs[i] = g.trace(segs)
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    for o in outs:
+        _compare(o, None, exp, exp_pos, "concurrent callers")
+    g.close()
+
+
 def test_errors(native, maps):
     m, _ = maps("kat0")
     g = native.BspGpu(m)
