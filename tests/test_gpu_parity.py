@@ -169,34 +169,55 @@ def test_position_to_leaf(native, maps, oracle_mod):
         g.close()
 
 
-def test_full_size_properties(native, maps, oracle_mod):
-    """C2 size (64M segments, generated on the device): the three staging variants must agree on
-    every result bit and on the hit count, and a strided sample must match the oracle."""
+@pytest.mark.parametrize("mapname,kind,n", [("rooms8", "uniform", 64 * 1024 * 1024), ("city10k", "long", 128 * 1024 * 1024)])
+def test_full_size_properties(native, maps, oracle_mod, mapname, kind, n):
+    """BASELINE.json sizes (C2: 64 Mi uniform segments on rooms8; C3: one GPU's 128 Mi-segment shard of the
+    1 Gi long segments on city10k), generated on the device.  Size-independent properties: every staging
+    variant and both kernels give the same bits and the same hit count; tracing twice is idempotent; the
+    hit counter equals the number of hit flags; a strided sample matches the oracle."""
     import torch
     from tools import mapgen, seggen
-    m, _ = maps("rooms8")
+    m, _ = maps(mapname)
     lo, hi = mapgen.seg_bounds(m)
-    n = 64 * 1024 * 1024
+    diag = float(np.sqrt(((hi - lo).astype(np.float64) ** 2).sum()))
     g = native.BspGpu(m)
     g.set_stream(torch.cuda.current_stream().cuda_stream)
     segs = torch.empty((n, 8), dtype=torch.float32, device="cuda")
-    g.generate(segs, 0, n, 0, 2, lo, hi)
-    outs, hits = [], []
-    for variant in (1, 2, 3):
-        g.set_option(1, variant)
+    first = 3 * n                                    # somewhere inside the global index space, like a rank's shard
+    if kind == "uniform":
+        g.generate(segs, first, n, 0, 2, lo, hi)
+    else:
+        g.generate(segs, first, n, 1, 3, lo, hi, 0.25 * diag, diag)
+    fits_smem = g.info()["map_bytes"] < 200 * 1024
+    configs = [(0, 0)] + ([(2, 0)] if fits_smem else []) + [(3, 0), (0, 1)]       # (variant, scheduler)
+    ref_out, ref_hits = None, None
+    for variant, sched in configs:
+        g.set_option(1, variant); g.set_option(9, sched)
         out = torch.empty((n, 4), dtype=torch.int32, device="cuda")
         g.trace(segs, out=out)
-        hits.append(g.hit_count())
-        outs.append(out)
-    assert hits[0] == hits[1] == hits[2]
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
-    assert int((outs[0][:, 3] & 1).sum().item()) == hits[0]
-    stride = 257
-    sample = segs[::stride].cpu().numpy()
-    assert np.array_equal(bits(sample), bits(seggen.uniform(2, 0, n, lo, hi)[::stride])) if n <= (1 << 22) else True
+        hits = g.hit_count()
+        if ref_out is None:
+            ref_out, ref_hits = out, hits
+            assert int((out[:, 3] & 1).sum().item()) == hits
+            again = torch.empty_like(out)
+            g.trace(segs, out=again)
+            assert torch.equal(out, again)                                        # idempotent
+            del again
+        else:
+            assert hits == ref_hits, (variant, sched)
+            assert torch.equal(out, ref_out), (variant, sched)
+            del out
+    stride = 4099
+    idx = torch.arange(0, n, stride, device="cuda")
+    sample = segs[idx].cpu().numpy()
+    gi = first + np.arange(0, n, stride, dtype=np.uint64)
+    # the sampled device segments are the generator's (seed, global index) floats
+    want = np.vstack([seggen.uniform(2, int(i), 1, lo, hi) if kind == "uniform" else seggen.long_rays(3, int(i), 1, lo, hi, 0.25 * diag, diag)
+                      for i in gi[:64]])
+    assert np.array_equal(bits(sample[:64]), bits(want))
     exp, _, _ = oracle_mod.Port(m).trace(sample)
-    got = outs[0][::stride].cpu().numpy().view(native.RESULT_DT).reshape(-1)
-    _compare(got, None, exp, None, "64M strided sample")
+    got = ref_out[idx].cpu().numpy().view(native.RESULT_DT).reshape(-1)
+    _compare(got, None, exp, None, f"{mapname} {n} strided sample")
     g.close()
 
 
