@@ -447,6 +447,15 @@ def run_ours(a):
         }
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_reference(w)
+        if world == 1 and a.also and a.also != a.workload:
+            # the other single-GPU configuration of BASELINE.json (configs[1]: rooms8, 64 Mi uniform segments, map staged
+            # in shared memory), device-resident, same timing rules -- reported beside the headline, not instead of it
+            try:
+                del segs, out
+                torch.cuda.empty_cache()
+                line["also"] = {a.also: secondary_workload(a.also, a, local, stream)}
+            except Exception as e:  # pragma: no cover
+                line["also"] = {a.also: {"error": str(e)}}
         print(json.dumps(line), flush=True)
 
     lib.bspgpu_host_free(h_in_ptr)
@@ -455,6 +464,39 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def secondary_workload(name, a, local, stream):
+    import torch
+    import bsp_b200
+    w2 = workload_setup(name)
+    n2 = 64 * 1024 * 1024
+    g2 = bsp_b200.BspGpu(w2["path"], device=local)
+    g2.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        segs2 = torch.empty((n2, 8), dtype=torch.float32, device="cuda")
+        out2 = torch.empty((n2, 4), dtype=torch.int32, device="cuda")
+        device_segments(g2, w2, segs2, 0, n2)
+        for _ in range(3):
+            g2.trace(segs2, out=out2, async_=True)
+        torch.cuda.synchronize()
+        steps = max(3, min(a.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            g2.trace(segs2, out=out2, async_=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    bpt = algorithmic_bytes(w2)
+    peak, _ = measured_peak()
+    info = g2.info()
+    res = {"value": n2 / (ms * 1e-3), "unit": "traces/s", "ms_per_step": ms, "steps": steps, "segments_per_step": n2,
+           "hits": g2.hit_count(), "bytes_per_trace": bpt["b_total"],
+           "roofline_frac": bpt["b_total"] * n2 / (ms * 1e-3) / 1e9 / peak,
+           "kernel": {"variant": info["variant"], "grid": info["grid_ctas"], "block": info["block_threads"], "smem": info["smem_bytes"]}}
+    g2.close()
+    return res
 
 
 def main():
@@ -467,6 +509,7 @@ def main():
     ap.add_argument("--segments-per-gpu", type=int, default=128 * 1024 * 1024)
     ap.add_argument("--e2e-segments", type=int, default=32 * 1024 * 1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--also", default="rooms8-uniform", help="second workload reported under 'also' at N=1 ('' to skip)")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--threads", type=int, default=None)
     ap.add_argument("--refill", type=int, default=None)
