@@ -48,6 +48,11 @@ TraceKernel pick_threads( int threads, int sched ) {
 		if( threads <= 512 ) return trace_persistent< M, S, 512 >;
 		return trace_persistent< M, S, 1024 >;
 	}
+	if( sched == 3 ) {   /* two segments per lane, one parked in shared memory */
+		if( threads <= 256 ) return trace_dual< M, S, 256 >;
+		if( threads <= 512 ) return trace_dual< M, S, 512 >;
+		return trace_dual< M, S, 1024 >;
+	}
 	if( sched == 2 ) {   /* experiment: 1536 threads per SM (<= 40 registers) */
 		if( threads <= 256 ) return trace_phased< M, S, 256, 6 >;
 		if( threads <= 512 ) return trace_phased< M, S, 512, 3 >;
@@ -92,7 +97,7 @@ struct bspgpu {
 	bool cfg_valid = false;
 	TraceKernel cfg_kernel = nullptr;
 	int cfg_variant = 0, cfg_mode = 0, cfg_threads = 0, cfg_grid = 0;
-	uint32_t cfg_smem = 0, cfg_top_nodes = 0;
+	uint32_t cfg_smem = 0, cfg_staged = 0, cfg_top_nodes = 0;
 
 	/* what the last trace did */
 	uint32_t last_variant = 0, last_threads = 0, last_grid = 0, last_smem = 0, last_launches = 0;
@@ -139,6 +144,11 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 		if( threads > 1024 ) threads = 1024;
 		if( h->opt_sched == 2 && threads > 768 ) threads = 768;
 
+		const uint32_t staged = smem;
+		if( h->opt_sched == 3 ) {
+			smem += 96u * ( uint32_t ) threads;   /* parking slots of trace_dual */
+			if( smem > ( uint32_t ) h->max_smem_optin ) return fail( BSPGPU_E_INVALID, "two-segment scheduler: staged map + 96 B/thread of parking slots exceed shared memory" );
+		}
 		TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched );
 		CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );
 		int ctas = ( int ) h->opt_ctas;
@@ -147,7 +157,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 		if( occ < 1 ) return fail( BSPGPU_E_CUDA, "kernel does not fit on an SM with the requested block size / shared memory" );
 		if( ctas <= 0 || ctas > occ ) ctas = occ;
 		h->cfg_kernel = kernel; h->cfg_variant = variant; h->cfg_mode = mode; h->cfg_threads = threads;
-		h->cfg_grid = h->sm_count * ctas; h->cfg_smem = smem; h->cfg_top_nodes = top_nodes;
+		h->cfg_grid = h->sm_count * ctas; h->cfg_smem = smem; h->cfg_staged = staged; h->cfg_top_nodes = top_nodes;
 		h->cfg_valid = true;
 	}
 	TraceKernel kernel = h->cfg_kernel;
@@ -157,7 +167,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 	TraceParams p;
 	p.image = h->d_image;
 	p.off_refs = h->lay.off_refs; p.off_sides = h->lay.off_sides; p.off_side_plane = h->lay.off_side_plane;
-	p.staged_bytes = smem; p.top_nodes = top_nodes;
+	p.staged_bytes = h->cfg_staged; p.top_nodes = top_nodes;
 	p.block_segs = ( uint32_t ) ( ( h->opt_block_segs + 31 ) / 32 * 32 );
 	p.refill = ( uint32_t ) ( h->opt_refill < 1 ? 1 : ( h->opt_refill > 32 ? 32 : h->opt_refill ) );
 	p.max_steps = ( uint32_t ) ( h->opt_max_steps < 1 ? ( mode == kSmemAll ? 16 : 8 ) : h->opt_max_steps );

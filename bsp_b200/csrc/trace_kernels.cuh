@@ -471,6 +471,210 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 	if( lane == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
 }
 
+/* ---------------------------------------------------------------- K1 with two segments per lane
+ *
+ * Two-phase scheduling of independent lanes tops out near 55 % SIMT utilisation: a lane is in one
+ * mode at a time and waits whenever its warp runs the other phase.  Here every lane owns TWO
+ * segments: one live in registers, one parked in shared memory (6 x 16 bytes per thread, laid
+ * out [word][thread] so a warp's accesses are conflict-free), each with its own traversal stack
+ * in local memory.  Before a phase, a lane whose live segment does not match the phase but whose
+ * parked one does swaps them (six LDS.128/STS.128 pairs through four temporaries).  A lane can
+ * then follow the warp's phase with probability 1-(1-p)^2 instead of p.  The arithmetic is
+ * untouched: the same lane_node_phase / lane_leaf_phase run on whichever segment is live.
+ * Costs 96 bytes of shared memory per thread on top of whatever is staged. */
+
+struct ParkSlot {
+	uint32_t base;       /* shared-window byte address of this thread's word 0 */
+	uint32_t stride;     /* bytes between consecutive words = 16 * blockDim.x */
+};
+
+__device__ __forceinline__ void sts128( uint32_t addr, float a, float b, float c, float d ) {
+	asm volatile( "st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"( addr ), "f"( a ), "f"( b ), "f"( c ), "f"( d ) : "memory" );
+}
+__device__ __forceinline__ float4 lds128v( uint32_t addr ) {
+	float4 v;
+	asm volatile( "ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"( v.x ), "=f"( v.y ), "=f"( v.z ), "=f"( v.w ) : "r"( addr ) : "memory" );
+	return v;
+}
+
+#define BSPK_SWAP4( k, a, b, c, d ) { \
+	const float4 t_ = lds128v( slot.base + ( k ) * slot.stride ); \
+	sts128( slot.base + ( k ) * slot.stride, a, b, c, d ); \
+	a = t_.x; b = t_.y; c = t_.z; d = t_.w; }
+
+/* exchange the live segment (registers) with the parked one (shared memory) */
+__device__ __forceinline__ void lane_swap( const ParkSlot & slot, Lane & l, uint32_t & seg ) {
+	float f_cur = __int_as_float( l.cur ), f_sp = __int_as_float( l.sp ), f_hflags = __uint_as_float( l.hflags );
+	float f_hside = __int_as_float( l.hside ), f_hbrush = __int_as_float( l.hbrush ), f_s = __uint_as_float( l.s );
+	float f_send = __uint_as_float( l.s_end ), f_brush = __int_as_float( l.brush ), f_bflags = __uint_as_float( l.bflags );
+	float f_fside = __int_as_float( l.far_side ), f_seg = __uint_as_float( seg ), f_pad0 = 0.0f, f_pad1 = 0.0f;
+	BSPK_SWAP4( 0, l.r.sx, l.r.sy, l.r.sz, l.r.dx )
+	BSPK_SWAP4( 1, l.r.dy, l.r.dz, l.tmin, l.tmax )
+	BSPK_SWAP4( 2, f_cur, f_sp, l.ht, f_hflags )
+	BSPK_SWAP4( 3, f_hside, f_hbrush, f_s, f_send )
+	BSPK_SWAP4( 4, f_brush, f_bflags, l.tfar, l.tnear )
+	BSPK_SWAP4( 5, f_fside, f_seg, f_pad0, f_pad1 )
+	l.cur = __float_as_int( f_cur ); l.sp = __float_as_int( f_sp ); l.hflags = __float_as_uint( f_hflags );
+	l.hside = __float_as_int( f_hside ); l.hbrush = __float_as_int( f_hbrush ); l.s = __float_as_uint( f_s );
+	l.s_end = __float_as_uint( f_send ); l.brush = __float_as_int( f_brush ); l.bflags = __float_as_uint( f_bflags );
+	l.far_side = __float_as_int( f_fside ); seg = __float_as_uint( f_seg );
+}
+
+__device__ __forceinline__ void lane_load_segment( const TraceParams & p, uint32_t sidx, Lane & l ) {
+	if( p.segs24 ) {
+		const float2 * sp24 = p.segs24 + ( size_t ) sidx * 3;
+		const float2 a = ld_stream2( sp24 ), b2 = ld_stream2( sp24 + 1 ), c = ld_stream2( sp24 + 2 );
+		lane_start( l, a.x, a.y, b2.x, b2.y, c.x, c.y );
+	}
+	else {
+		const float4 a = ld_stream4( p.segs + ( size_t ) sidx * 2 );
+		const float4 b4 = ld_stream4( p.segs + ( size_t ) sidx * 2 + 1 );
+		lane_start( l, a.x, a.y, a.z, b4.x, b4.y, b4.z );
+	}
+}
+
+template< int kMode, int kStack, int kMaxThreads >
+__global__ void __launch_bounds__( kMaxThreads, 1 ) trace_dual( const TraceParams p ) {
+	extern __shared__ __align__( 128 ) unsigned char smem[];
+	__shared__ __align__( 8 ) uint64_t stage_bar;
+
+	if( kMode != kGlobal && p.staged_bytes > 0 ) {
+		if( threadIdx.x == 0 ) {
+			mbar_init( &stage_bar, 1 );
+			mbar_fence_init();
+		}
+		__syncthreads();
+		if( threadIdx.x == 0 ) {
+			mbar_expect_tx( &stage_bar, p.staged_bytes );
+			const uint32_t kChunk = 32768;
+			for( uint32_t off = 0; off < p.staged_bytes; off += kChunk ) {
+				const uint32_t sz = min( kChunk, p.staged_bytes - off );
+				bulk_g2s( smem + off, p.image + off, sz, &stage_bar );
+			}
+		}
+		mbar_wait( &stage_bar, 0 );
+	}
+
+	typename MapOf< kMode >::type map;
+	const NodeRec * g_nodes = reinterpret_cast< const NodeRec * >( p.image );
+	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
+	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
+	if constexpr( kMode == kSmemAll ) {
+		map.nodes = opaque_u32( smem_u32( smem ) );
+		map.refs = opaque_u32( map.nodes + ( uint32_t ) p.off_refs );
+		map.sides = opaque_u32( map.nodes + ( uint32_t ) p.off_sides );
+	}
+	else if constexpr( kMode == kSmemTop ) {
+		map.top = opaque_u32( smem_u32( smem ) );
+		map.top_nodes = p.top_nodes;
+		map.g.nodes = g_nodes; map.g.refs = g_refs; map.g.sides = g_sides;
+	}
+	else {
+		map.nodes = g_nodes; map.refs = g_refs; map.sides = g_sides;
+	}
+	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
+
+	/* parking area right behind the staged bytes (sections are 128-byte aligned) */
+	ParkSlot slot;
+	slot.stride = 16u * blockDim.x;
+	slot.base = opaque_u32( smem_u32( smem ) + p.staged_bytes + 16u * threadIdx.x );
+
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = ( 1u << lane ) - 1u;
+	const unsigned kFull = 0xffffffffu;
+
+	uint32_t blk_next = 0, blk_end = 0;
+	bool more_work = true;
+
+	Lane l;
+	lane_start( l, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f );
+	l.cur = kCurIdle;
+	l.brush = -1; l.bflags = 0; l.tfar = l.tnear = 0.0f; l.far_side = -1;
+	uint32_t seg = 0, my_hits = 0;
+	/* the parked slot starts out idle: write one idle state (cur == kCurIdle) into it.
+	 * Invariant from here on: the slot always holds a complete state and its `cur` word == pcur. */
+	lane_swap( slot, l, seg );
+	l.cur = kCurIdle;
+	int32_t pcur = kCurIdle;
+	uint32_t which = 0;                   /* which local stack belongs to the live segment */
+	StackEntry16 stacks[ 2 ][ kStack ];
+
+	for( ;; ) {
+		/* ---- work fetch: every empty slot (live first, then parked) takes a new segment */
+		const bool live_idle = l.cur == kCurIdle, park_idle = pcur == kCurIdle;
+		const unsigned m_live = __ballot_sync( kFull, live_idle );
+		const unsigned m_park = __ballot_sync( kFull, park_idle );
+		const uint32_t n_live = __popc( m_live ), n_want = n_live + __popc( m_park );
+		if( more_work && n_want >= p.refill ) {
+			if( blk_next == blk_end ) {
+				unsigned long long b = 0;
+				if( lane == 0 ) b = atomicAdd( p.next, ( unsigned long long ) p.block_segs );
+				b = __shfl_sync( kFull, b, 0 );
+				if( b >= ( unsigned long long ) p.n ) more_work = false;
+				else {
+					blk_next = ( uint32_t ) b;
+					blk_end = ( uint32_t ) min( b + ( unsigned long long ) p.block_segs, ( unsigned long long ) p.n );
+				}
+			}
+			if( more_work ) {
+				const uint32_t avail = blk_end - blk_next;
+				const uint32_t rank_live = __popc( m_live & lt_mask );
+				const uint32_t rank_park = n_live + __popc( m_park & lt_mask );
+				if( live_idle && rank_live < avail ) {
+					seg = blk_next + rank_live;
+					lane_load_segment( p, seg, l );
+				}
+				if( park_idle && rank_park < avail ) {
+					/* move whatever is live (old or just started) to the parked slot, start the new one live */
+					const int32_t old_cur = l.cur;
+					lane_swap( slot, l, seg );
+					pcur = old_cur; which ^= 1u;
+					seg = blk_next + rank_park;
+					lane_load_segment( p, seg, l );
+				}
+				blk_next += min( n_want, avail );
+			}
+		}
+
+		/* ---- pick the phase most lanes can follow with one of their two segments */
+		const bool live_node = lane_in_node( l ), live_leaf = lane_in_leaf( l );
+		const bool park_node = pcur >= 0, park_leaf = ( uint32_t ) pcur > ( uint32_t ) kCurDone;
+		const unsigned can_node = __ballot_sync( kFull, live_node || park_node );
+		const unsigned can_leaf = __ballot_sync( kFull, live_leaf || park_leaf );
+		if( ( can_node | can_leaf ) == 0u ) {
+			if( !more_work ) break;
+			continue;
+		}
+		const bool leaf_phase = can_node == 0u || ( uint32_t ) __popc( can_leaf ) >= p.leaf_threshold;
+		if( leaf_phase ? ( !live_leaf && park_leaf ) : ( !live_node && park_node ) ) {
+			const int32_t old_cur = l.cur;
+			lane_swap( slot, l, seg );
+			pcur = old_cur; which ^= 1u;
+		}
+		StackEntry16 * stack = stacks[ which ];
+		if( leaf_phase ) lane_leaf_phase( map, l, stack, p.side_steps );
+		else lane_node_phase( map, l, stack, p.max_steps );
+
+		/* ---- retire finished segments */
+		if( lane_done( l ) ) {
+			HitState h;
+			lane_hit_state( l, h );
+			const ResultRec o = make_result( h, side_plane );
+			if( p.out ) st_stream4( p.out + seg, o.t, __int_as_float( o.plane ), __int_as_float( o.brush ), __uint_as_float( o.flags ) );
+			if( p.pos ) {
+				float px, py, pz;
+				make_pos( l.r, h, px, py, pz );                                 /* bsp.cc:265-267 */
+				st_stream4( p.pos + seg, px, py, pz, h.t );
+			}
+			my_hits += ( uint32_t ) h.hit;
+			l.cur = kCurIdle;
+		}
+	}
+
+	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( kFull, my_hits, o );
+	if( lane == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
+}
+
 /* ---------------------------------------------------------------- N3: batched position_to_leaf */
 
 __global__ void leaf_kernel( const unsigned char * image, const float * pts, uint32_t stride, uint64_t n, int32_t * leaf_out ) {

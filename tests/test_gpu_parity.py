@@ -349,3 +349,23 @@ def test_depth_frame_demo(native, maps, oracle_mod):
         assert np.array_equal(bits(t.reshape(-1)), bits(exp["t"]))
         assert np.array_equal(hit.reshape(-1), (exp["flags"] & 1).astype(bool))
     g.close()
+
+
+@pytest.mark.parametrize("mapname,variant", [("rooms8", 1), ("rooms8", 3), ("city10k", 3), ("kat1", 1)])
+def test_two_segment_scheduler(native, maps, oracle_mod, mapname, variant):
+    """BSPGPU_OPT_SCHEDULER=3: every lane owns two segments (one parked in shared memory)."""
+    m, _ = maps(mapname)
+    segs = _segments(m, 200_000, 150_000, 50_000, 8192)
+    exp, exp_pos, ctr = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    g.set_option(9, 3); g.set_option(1, variant)
+    for threads, refill, steps, side, thr in ((0, 8, 0, 8, 16), (128, 1, 1, 1, 1), (512, 32, 1000, 1000, 32)):
+        g.set_option(2, threads); g.set_option(6, refill); g.set_option(7, steps); g.set_option(10, side); g.set_option(11, thr)
+        pos = np.zeros((len(segs), 4), np.float32)
+        res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+        _compare(res, pos, exp, exp_pos, f"dual {mapname} v{variant} {threads}/{refill}/{steps}/{side}/{thr}")
+        assert g.hit_count() == ctr["hits"]
+    for n in (1, 31, 33, 65, 1000):
+        res = g.trace(segs[:n])
+        _compare(res, None, exp[:n], None, f"dual n={n}")
+    g.close()
