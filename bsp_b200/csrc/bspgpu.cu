@@ -35,6 +35,12 @@ int fail( int code, const std::string & msg ) { g_err = msg; return code; }
 #define CK( call ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) { \
 	return fail( BSPGPU_E_CUDA, std::string( #call ) + ": " + cudaGetErrorString( e_ ) ); } } while( 0 )
 
+/* device scratch that is released on every exit path */
+struct DeviceScratch {
+	void * p = nullptr;
+	~DeviceScratch() { if( p ) cudaFree( p ); }
+};
+
 const int kBufs = 3;
 const int kCounterSlots = 64;               /* one work counter per in-flight launch */
 const uint64_t kMaxLaunchSegs = 1ull << 30; /* in-kernel segment indices are 32-bit */
@@ -417,21 +423,22 @@ int bspgpu_leaf( bspgpu_t * h, const float * pts, uint32_t stride, uint64_t n, i
 	CK( cudaSetDevice( h->device ) );
 	cudaStream_t st = h->stream();
 	const bool pts_dev = ( flags & BSPGPU_SEGS_DEVICE ) != 0, out_dev = ( flags & BSPGPU_OUT_DEVICE ) != 0;
-	float * d_pts = nullptr; int32_t * d_leaf = nullptr;
+	DeviceScratch s_pts, s_leaf;
 	if( !pts_dev ) {
-		CK( cudaMalloc( &d_pts, n * stride * sizeof( float ) ) );
-		CK( cudaMemcpyAsync( d_pts, pts, n * stride * sizeof( float ), cudaMemcpyHostToDevice, st ) );
+		CK( cudaMalloc( &s_pts.p, n * stride * sizeof( float ) ) );
+		CK( cudaMemcpyAsync( s_pts.p, pts, n * stride * sizeof( float ), cudaMemcpyHostToDevice, st ) );
 	}
-	if( !out_dev ) CK( cudaMalloc( &d_leaf, n * sizeof( int32_t ) ) );
+	if( !out_dev ) CK( cudaMalloc( &s_leaf.p, n * sizeof( int32_t ) ) );
+	const float * k_pts = pts_dev ? pts : ( const float * ) s_pts.p;
+	int32_t * k_leaf = out_dev ? leaf : ( int32_t * ) s_leaf.p;
 	const int threads = 256;
 	uint64_t blocks = ( n + threads - 1 ) / threads;
 	if( blocks > ( uint64_t ) h->sm_count * 16 ) blocks = ( uint64_t ) h->sm_count * 16;
-	leaf_kernel<<< ( unsigned ) blocks, threads, 0, st >>>( h->d_image, pts_dev ? pts : d_pts, stride, n, out_dev ? leaf : d_leaf );
+	leaf_kernel<<< ( unsigned ) blocks, threads, 0, st >>>( h->d_image, k_pts, stride, n, k_leaf );
 	CK( cudaGetLastError() );
-	if( !out_dev ) CK( cudaMemcpyAsync( leaf, d_leaf, n * sizeof( int32_t ), cudaMemcpyDeviceToHost, st ) );
+	if( !out_dev ) CK( cudaMemcpyAsync( leaf, k_leaf, n * sizeof( int32_t ), cudaMemcpyDeviceToHost, st ) );
+	/* scratch is freed when this function returns, so wait unless the caller owns every buffer */
 	if( !( ( flags & BSPGPU_ASYNC ) && pts_dev && out_dev ) ) CK( cudaStreamSynchronize( st ) );
-	if( d_pts ) cudaFree( d_pts );
-	if( d_leaf ) cudaFree( d_leaf );
 	return BSPGPU_OK;
 }
 
@@ -449,11 +456,13 @@ int bspgpu_generate( bspgpu_t * h, const bspgpu_gen_desc * g, uint64_t first, ui
 	for( int a = 0; a < 3; a++ ) { p.lo[ a ] = g->lo[ a ]; p.ext[ a ] = g->hi[ a ] - g->lo[ a ]; }
 	p.len_lo = g->len_lo; p.len_ext = g->len_hi - g->len_lo;
 	p.first = first; p.count = count; p.out = reinterpret_cast< float4 * >( dev_segs );
+	DeviceScratch s_views;
 	float * d_views = nullptr;
 	if( g->kind == 2 ) {
 		if( !g->views || !g->num_views || !g->width || !g->height ) return fail( BSPGPU_E_INVALID, "bspgpu_generate: camera kind needs views and a grid size" );
 		if( first + count > ( uint64_t ) g->num_views * g->width * g->height ) return fail( BSPGPU_E_INVALID, "bspgpu_generate: camera range exceeds views*width*height" );
-		CK( cudaMalloc( &d_views, ( size_t ) g->num_views * 12 * sizeof( float ) ) );
+		CK( cudaMalloc( &s_views.p, ( size_t ) g->num_views * 12 * sizeof( float ) ) );
+		d_views = ( float * ) s_views.p;
 		CK( cudaMemcpyAsync( d_views, g->views, ( size_t ) g->num_views * 12 * sizeof( float ), cudaMemcpyHostToDevice, st ) );
 		p.views = d_views; p.width = g->width; p.height = g->height;
 		p.inv2w = ( float ) ( 2.0 / ( double ) g->width ); p.inv2h = ( float ) ( 2.0 / ( double ) g->height );
@@ -466,7 +475,6 @@ int bspgpu_generate( bspgpu_t * h, const bspgpu_gen_desc * g, uint64_t first, ui
 	generate_kernel<<< ( unsigned ) blocks, threads, 0, st >>>( p );
 	CK( cudaGetLastError() );
 	CK( cudaStreamSynchronize( st ) );
-	if( d_views ) cudaFree( d_views );
 	return BSPGPU_OK;
 }
 

@@ -1,22 +1,30 @@
 /*
  * trace_kernels.cuh -- sm_100a kernels of the batched segment trace.
  *
- * K1/K2  trace_persistent<Mode>: persistent warps.  Each warp owns a private block of
- *        consecutive segments claimed with one global atomicAdd (warp-level work fetch);
- *        lanes whose segment has finished are re-filled from that block as soon as
- *        `refill` lanes are idle (__ballot_sync / __popc ranks = the ray compaction), so a
- *        warp keeps ~32 live segments instead of waiting for its slowest one.
- *        The per-lane walk is trace_core.h (the reference's statements, one rounding each).
- *        Mode kSmemAll : the whole flattened map [nodes|refs|sides] is staged in shared
- *                        memory with cp.async.bulk (TMA 1-D bulk copy) + an mbarrier  (C1/C2)
- *             kSmemTop : only the first `top_nodes` breadth-first nodes are staged; the rest
- *                        of the map is read through the read-only path (L1 -> L2)       (C3-C5)
- *             kGlobal  : nothing staged.
- * K3     hit count: per-lane counters, one shuffle reduction + one atomicAdd per warp.
- * N3     leaf_kernel: batched BSP::position_to_leaf (reference bsp.cc:273-286).
+ * All three trace kernels are persistent: each warp claims a private block of consecutive
+ * segments with one global atomicAdd (warp-level work fetch) and re-fills lanes whose segment
+ * has finished from that block as soon as `refill` lanes are idle (__ballot_sync / __popc ranks
+ * = the ray compaction), so a warp keeps ~32 live segments instead of waiting for its slowest
+ * one.  The per-lane arithmetic is trace_core.h (the reference's statements, one rounding each).
  *
- * No tensor cores: the walk is a dependent chain of 16/32-byte gathers and a handful of
- * fp32 ops per node/side, not a contraction.
+ *   trace_phased      THE SHIPPED KERNEL.  Lanes are resumable node/leaf state machines; each warp
+ *                     iteration runs the one bounded phase most of its lanes wait for.
+ *   trace_persistent  the first version (rounds: every lane descends to a leaf, then every lane
+ *                     clips its leaf).  Kept selectable (BSPGPU_OPT_SCHEDULER=1) as a cross-check.
+ *   trace_dual        experiment (BSPGPU_OPT_SCHEDULER=3): two segments per lane, one parked in
+ *                     shared memory.  Higher SIMT utilisation, but loses to L1 capacity on rooms8.
+ *
+ * Map staging (template `kMode`):
+ *   kSmemAll : the whole flattened map [nodes|refs|sides] is copied into shared memory with
+ *              cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) completing on an mbarrier   (C1/C2)
+ *   kSmemTop : only the first `top_nodes` breadth-first nodes are staged; the rest of the map is
+ *              read through the read-only path (L1 -> L2)
+ *   kGlobal  : nothing staged; a node is one 256-bit read-only load                      (C3-C5)
+ * K3  hit count: per-lane counters, one shuffle reduction + one atomicAdd per warp.
+ * N3  leaf_kernel: batched BSP::position_to_leaf (reference bsp.cc:273-286).
+ *
+ * No tensor cores: the walk is a dependent chain of 16/32-byte gathers and a handful of fp32
+ * ops per node/side, not a contraction.
  */
 #ifndef BSPGPU_TRACE_KERNELS_CUH
 #define BSPGPU_TRACE_KERNELS_CUH
