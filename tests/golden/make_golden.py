@@ -20,7 +20,7 @@ def main():
     from tools import ibsp, mapgen, seggen
     oracle.build()
     assert oracle.have_reference(), "needs /root/reference"
-    for name, n_edge, n_rand in (("kat0", 512, 1024), ("kat1", 1024, 2048), ("rooms8", 4096, 8192)):
+    for name, n_edge, n_rand in (("kat0", 512, 1024), ("kat1", 1024, 2048), ("rooms8", 4096, 8192), ("tilted", 2048, 6144)):
         m, path = mapgen.get_map(name)
         lo, hi = mapgen.seg_bounds(m)
         diag = float(np.sqrt(((hi - lo).astype(np.float64) ** 2).sum()))

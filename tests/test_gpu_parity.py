@@ -61,7 +61,7 @@ def test_kat_vectors(native, maps):
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))
-@pytest.mark.parametrize("mapname", ["kat1", "rooms8", "city10k"])
+@pytest.mark.parametrize("mapname", ["kat1", "rooms8", "city10k", "tilted"])
 def test_parity_vs_oracle(native, maps, oracle_mod, mapname, variant):
     m, path = maps(mapname)
     g = native.BspGpu(m)
@@ -256,7 +256,7 @@ def test_errors(native, maps):
     g.close()
 
 
-@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8"])
+@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "tilted"])
 def test_golden_reference_outputs(native, name):
     """committed fixtures = outputs of the unmodified reference (tests/golden/make_golden.py)."""
     from helpers import load_golden
@@ -270,8 +270,9 @@ def test_golden_reference_outputs(native, name):
     g.close()
 
 
-def test_both_schedulers_agree(native, maps, oracle_mod):
-    m, _ = maps("city10k")
+@pytest.mark.parametrize("mapname", ["city10k", "tilted"])
+def test_both_schedulers_agree(native, maps, oracle_mod, mapname):
+    m, _ = maps(mapname)
     segs = _segments(m, 100_000, 200_000, 50_000, 4096)
     exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
     g = native.BspGpu(m)
@@ -351,7 +352,7 @@ def test_depth_frame_demo(native, maps, oracle_mod):
     g.close()
 
 
-@pytest.mark.parametrize("mapname,variant", [("rooms8", 1), ("rooms8", 3), ("city10k", 3), ("kat1", 1)])
+@pytest.mark.parametrize("mapname,variant", [("rooms8", 1), ("rooms8", 3), ("city10k", 3), ("kat1", 1), ("tilted", 1)])
 def test_two_segment_scheduler(native, maps, oracle_mod, mapname, variant):
     """BSPGPU_OPT_SCHEDULER=3: every lane owns two segments (one parked in shared memory)."""
     m, _ = maps(mapname)

@@ -14,7 +14,7 @@ def _check(res, pos, exp, exp_pos, what):
     assert not badp.any(), f"{what}: {int(badp.sum())} pos mismatches"
 
 
-@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "city10k"])
+@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "city10k", "tilted"])
 def test_core_matches_oracle(oracle_mod, maps, name):
     m, _ = maps(name)
     segs = mixed_segments(m, 100_000, 100_000, 50_000, 8192)
@@ -27,7 +27,7 @@ def test_core_matches_oracle(oracle_mod, maps, name):
         _check(res, pos, exp, exp_pos, f"{name} phased {budgets}")
 
 
-@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8"])
+@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "tilted"])
 def test_core_matches_golden_reference_outputs(name):
     m, segs, hit, t, pos = load_golden(name)
     res, p = HostSim(m).trace(segs, (0, 0))

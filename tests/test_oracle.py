@@ -47,7 +47,7 @@ def test_kat_quirks_are_kept(oracle_mod, maps):
     assert (res["flags"][0] & 1) and res["t"][0] == 0.5 and res["plane"][0] == -1   # hit reported at tmin, no side raised tfar
 
 
-@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8"])
+@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "tilted"])
 def test_port_matches_golden_reference_outputs(oracle_mod, name):
     m, segs, hit, t, pos = load_golden(name)
     res, ppos, ctr = oracle_mod.Port(m).trace(segs)
@@ -57,7 +57,7 @@ def test_port_matches_golden_reference_outputs(oracle_mod, name):
     assert ctr["hits"] == int(hit.sum())
 
 
-@pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k"])
+@pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k", "tilted"])
 def test_port_matches_reference_object(oracle_mod, maps, name):
     if not oracle_mod.have_reference():
         pytest.skip("reference object not built on this box")

@@ -580,7 +580,105 @@ def mega200k(seed: int = 5) -> ibsp.IBSP:
                  roof_num=1, roof_den=50, seed=seed, name="mega200k")
 
 
-MAPS = {"kat0": kat0, "kat1": kat1, "rooms8": rooms8, "city10k": city10k, "mega200k": mega200k}
+def _brush_corners(bmin, bmax):
+    xs = np.array([[bmin[0], bmax[0]][i & 1] for i in range(8)])
+    ys = np.array([[bmin[1], bmax[1]][(i >> 1) & 1] for i in range(8)])
+    zs = np.array([[bmin[2], bmax[2]][(i >> 2) & 1] for i in range(8)])
+    return np.stack((xs, ys, zs), axis=1)
+
+
+def tilted(seed: int = 9, n_brushes: int = 260, leaf_max: int = 1, max_depth: int = 60) -> ibsp.IBSP:
+    """Q3-style tree: node planes are taken from BRUSH SIDES, so most of them are non-axial (the kd
+    compiler above only ever emits axial splits, real q3map output does not), the tree is unbalanced
+    and deeper than 32 levels (exercises the 64-entry traversal stack).  Brushes: rotated pillars,
+    ramps, roofs and boxes scattered in a 2048^3 cube; classification against a split plane uses the
+    eight AABB corners (conservative)."""
+    rng = Rng(seed)
+    bl = BrushList()
+    W = 1024
+    for k in range(n_brushes):
+        cx, cy, cz = rng.randint(-W + 100, W - 100), rng.randint(-W + 100, W - 100), rng.randint(-W + 100, W - 100)
+        kind = rng.randint(0, 5) % 4              # pillars twice as likely: most side planes non-axial
+        tex = TEX_NONSOLID if rng.chance(1, 12) else (TEX_SOLID_PLUS if rng.chance(1, 8) else TEX_SOLID)
+        if kind == 0:
+            bl.pillar(cx, cy, rng.randint(8, 60), cz - rng.randint(8, 90), cz + rng.randint(8, 90), ROTATIONS[rng.randint(0, len(ROTATIONS) - 1)], tex)
+        elif kind == 1:
+            sx, sy, sz = rng.randint(20, 120), rng.randint(20, 120), rng.randint(10, 100)
+            bl.ramp(cx, cx + sx, cy, cy + sy, cz, cz + sz, along_x=rng.chance(1, 2), texture=tex)
+        elif kind == 2:
+            sx, sy, sz = rng.randint(20, 120), rng.randint(20, 120), rng.randint(10, 80)
+            bl.roof(cx, cx + sx, cy, cy + sy, cz, cz + sz, ridge_along_x=rng.chance(1, 2), texture=tex)
+        else:
+            sx, sy, sz = rng.randint(10, 90), rng.randint(10, 90), rng.randint(10, 90)
+            bl.box(cx, cx + sx, cy, cy + sy, cz, cz + sz, tex)
+    nb = len(bl)
+    bmin = np.asarray(bl.bmin, np.float64); bmax = np.asarray(bl.bmax, np.float64)
+    corners = np.stack([_brush_corners(bmin[i], bmax[i]) for i in range(nb)])          # (nb, 8, 3)
+    planes64 = np.asarray(bl.planes, np.float64)
+    first = np.asarray(bl.first_side); nsides = np.asarray(bl.num_sides); side_planes = np.asarray(bl.side_planes)
+
+    nodes, leaves = [], []
+    stats = {"max_depth": 0}
+
+    def leaf(ids, depth):
+        leaves.append(np.sort(ids)); stats["max_depth"] = max(stats["max_depth"], depth)
+        return -len(leaves)
+
+    work = [(np.arange(nb), 0, -1, 0)]
+    while work:
+        ids, depth, parent, slot = work.pop()
+        ref = None
+        if len(ids) <= leaf_max or depth >= max_depth:
+            ref = leaf(ids, depth)
+        else:
+            chosen = None
+            lopsided = rng.chance(7, 8)               # most splits peel off as little as possible: a deep, unbalanced tree
+            for _ in range(24):                       # a few random candidate side planes (non-axial preferred)
+                b = int(ids[rng.randint(0, len(ids) - 1)])
+                pidx = int(side_planes[first[b] + rng.randint(0, int(nsides[b]) - 1)])
+                n, d = planes64[pidx, :3], planes64[pidx, 3]
+                if np.abs(n).max() == 1.0 and rng.chance(3, 4):
+                    continue
+                dist = corners[ids] @ n - d            # (k, 8)
+                in_front = dist.max(axis=1) > 1e-6
+                in_back = dist.min(axis=1) < -1e-6
+                nf, nbk = int(in_front.sum()), int(in_back.sum())
+                if max(nf, nbk) < len(ids):
+                    score = max(nf, nbk) + (nf + nbk - len(ids))
+                    if lopsided:
+                        score = -max(nf, nbk)
+                    if chosen is None or score < chosen[0]:
+                        chosen = (score, pidx, ids[in_front], ids[in_back | ~in_front])
+            if chosen is None:
+                ref = leaf(ids, depth)
+            else:
+                ref = len(nodes)
+                nodes.append([chosen[1], 0, 0])
+                work.append((chosen[3], depth + 1, ref, 1))
+                work.append((chosen[2], depth + 1, ref, 0))
+        if parent >= 0:
+            nodes[parent][1 + slot] = ref
+    node_arr = np.zeros(len(nodes), ibsp.NODE_DT)
+    for i, (pidx, c0, c1) in enumerate(nodes):
+        node_arr[i] = (pidx, (c0, c1), (0, 0, 0), (0, 0, 0))
+    leaf_arr = np.zeros(len(leaves), ibsp.LEAF_DT)
+    off = 0
+    for i, ids in enumerate(leaves):
+        leaf_arr[i]["first_brush"] = off; leaf_arr[i]["num_brushes"] = len(ids); off += len(ids)
+    plane_arr = np.zeros(len(bl.planes), ibsp.PLANE_DT)
+    p32 = np.asarray(bl.planes, np.float32)
+    plane_arr["n"] = p32[:, :3]; plane_arr["d"] = p32[:, 3]
+    brush_arr = np.zeros(nb, ibsp.BRUSH_DT)
+    brush_arr["first_side"] = first; brush_arr["num_sides"] = nsides; brush_arr["texture"] = np.asarray(bl.texture, np.int32)
+    side_arr = np.zeros(len(bl.side_planes), ibsp.BRUSHSIDE_DT)
+    side_arr["plane"] = side_planes
+    side_arr["texture"] = np.repeat(np.asarray(bl.texture, np.int32), nsides)
+    meta = {"name": "tilted", "max_depth": stats["max_depth"], "world_min": [-W - 150.0] * 3, "world_max": [W + 150.0] * 3}
+    return ibsp.IBSP(_textures_array(DEFAULT_TEXTURES), plane_arr, node_arr, leaf_arr,
+                     np.concatenate(leaves).astype(np.uint32), brush_arr, side_arr, meta)
+
+
+MAPS = {"kat0": kat0, "kat1": kat1, "rooms8": rooms8, "city10k": city10k, "mega200k": mega200k, "tilted": tilted}
 
 
 def cache_dir() -> str:
