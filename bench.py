@@ -185,10 +185,15 @@ def measured_peak():
 def algorithmic_bytes(w, sample=200_000):
     """B = 48 + 28 n_node + 8 n_leaf + 12 n_lb + 8 n_solid + 20 n_side, visit-count
     means from the oracle port (the checker, run on a sample of this workload -- not the measured path)."""
-    import oracle
-    segs = host_segments(w, 0, sample)
-    _, _, ctr = oracle.Port(w["m"]).trace(segs, want_pos=False)
-    return oracle.bytes_per_trace(ctr, b_io=48)
+    try:
+        import oracle
+        segs = host_segments(w, 0, sample)
+        _, _, ctr = oracle.Port(w["m"]).trace(segs, want_pos=False)
+        return oracle.bytes_per_trace(ctr, b_io=48)
+    except Exception as e:  # pragma: no cover -- checker not buildable on this box: use the committed visit-count means
+        log(f"bench.py: oracle port unavailable ({e}); using profiles/bytes_per_trace.json")
+        rec = json.load(open(os.path.join(ROOT, "profiles", "bytes_per_trace.json")))[w["map"] + "/" + w["kind"]]
+        return {"b_io": 48, "b_map": rec["b_total"] - 48, "b_total": rec["b_total"], "means": rec["means"], "hit_rate": rec.get("hit_rate")}
 
 
 def cpu_reference(w, seconds_budget=12.0, threads=None):
