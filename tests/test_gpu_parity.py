@@ -397,3 +397,33 @@ def test_extreme_float_inputs(native, maps, oracle_mod):
         finite = np.isfinite(exp_pos).all(axis=1)
         assert np.array_equal(bits(pos[finite, :3]), bits(exp_pos[finite]))
     g.close()
+
+
+def test_mixed_pointer_kinds_and_pos_only(native, maps, oracle_mod):
+    """segments in HBM + results to host, segments on host + results in HBM, and pos-only output."""
+    import ctypes as C
+    import torch
+    m, _ = maps("rooms8")
+    segs = _segments(m, 120_000, 40_000, 20_000, 4096)
+    n = len(segs)
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    g.set_option(5, 30_000)
+    lib = native.load_library()
+    d_segs = torch.from_numpy(segs).cuda()
+    # device segments -> host results
+    res = np.zeros(n, native.RESULT_DT)
+    assert lib.bspgpu_trace(g.h, d_segs.data_ptr(), n, res.ctypes.data, 1) == 0          # BSPGPU_SEGS_DEVICE
+    _compare(res, None, exp, None, "device segs, host out")
+    # host segments -> device results
+    d_out = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    assert lib.bspgpu_trace(g.h, segs.ctypes.data, n, d_out.data_ptr(), 2) == 0           # BSPGPU_OUT_DEVICE
+    torch.cuda.synchronize()
+    _compare(d_out.cpu().numpy().view(native.RESULT_DT).reshape(-1), None, exp, None, "host segs, device out")
+    # pos only
+    pos = np.zeros((n, 4), np.float32)
+    assert lib.bspgpu_trace_pos(g.h, segs.ctypes.data, n, None, pos.ctypes.data, 0) == 0
+    assert np.array_equal(bits(pos[:, :3]), bits(exp_pos)) and np.array_equal(bits(pos[:, 3]), bits(exp["t"]))
+    # ASYNC is refused for host pointers
+    assert lib.bspgpu_trace(g.h, segs.ctypes.data, n, res.ctypes.data, 8) < 0
+    g.close()
