@@ -18,10 +18,13 @@ collective -- NCCL carries only the per-step hit-count all-reduce and a small re
             max over ranks.
 `e2e`     : the same metric through the public C-ABI call with HOST (pinned) buffers: every
             step copies that step's segments H2D and its results D2H inside the timed region.
-`roofline`: algorithmic bytes per trace (BASELINE.md section 5 formula, visit counts measured by
-            the oracle port on a sample of this workload) x traces per launch / mean launch time.
+`roofline`: algorithmic bytes per trace (BASELINE.md section 5 formula; visit-count means from the
+            counter-instrumented CPU restatement) x traces per launch / mean launch time.
 `cpu_baseline`: the unmodified reference (oracle/_ref), work_queue-threaded on all host cores,
-            on a bounded sample of the same workload (rank 0, N=1 only).
+            on a bounded sample of the same workload (rank 0, N=1 only).  This leg is the ONLY place
+            the arm touches oracle/: it also refreshes the visit counts and spot-checks a sample of the
+            timed run's results; without it (N>1, --no-cpu) the committed counts in
+            profiles/bytes_per_trace.json are used and no checker runs.
 """
 from __future__ import annotations
 
@@ -182,23 +185,34 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def algorithmic_bytes(w, sample=200_000):
-    """B = 48 + 28 n_node + 8 n_leaf + 12 n_lb + 8 n_solid + 20 n_side, visit-count
-    means from the oracle port (the checker, run on a sample of this workload -- not the measured path)."""
-    try:
-        import oracle
-        segs = host_segments(w, 0, sample)
-        _, _, ctr = oracle.Port(w["m"]).trace(segs, want_pos=False)
-        return oracle.bytes_per_trace(ctr, b_io=48)
-    except Exception as e:  # pragma: no cover -- checker not buildable on this box: use the committed visit-count means
-        log(f"bench.py: oracle port unavailable ({e}); using profiles/bytes_per_trace.json")
-        rec = json.load(open(os.path.join(ROOT, "profiles", "bytes_per_trace.json")))[w["map"] + "/" + w["kind"]]
-        return {"b_io": 48, "b_map": rec["b_total"] - 48, "b_total": rec["b_total"], "means": rec["means"], "hit_rate": rec.get("hit_rate")}
+def algorithmic_bytes(w, counters=None):
+    """B = 48 + 28 n_node + 8 n_leaf + 12 n_lb + 8 n_solid + 20 n_side.
+    Visit-count means come from the counter-instrumented CPU restatement: measured live by the cpu_baseline
+    leg when it runs (N=1), otherwise the committed means of profiles/bytes_per_trace.json (same generator,
+    same seed -- written from earlier cpu_baseline legs).  The product path never touches the oracle."""
+    if counters is not None:
+        n = max(1, counters["traces"])
+        mean = {k: counters[k] / n for k in ("nodes", "leaves", "leaf_brushes", "solid", "sides")}
+        b_map = 28 * mean["nodes"] + 8 * mean["leaves"] + 12 * mean["leaf_brushes"] + 8 * mean["solid"] + 20 * mean["sides"]
+        return {"b_io": 48, "b_map": b_map, "b_total": 48 + b_map, "means": mean, "source": "cpu_baseline leg (oracle port counters on 200000 segments of this workload)"}
+    rec = json.load(open(os.path.join(ROOT, "profiles", "bytes_per_trace.json")))[w["map"] + "/" + w["kind"]]
+    return {"b_io": 48, "b_map": rec["b_total"] - 48, "b_total": rec["b_total"], "means": rec["means"], "source": "profiles/bytes_per_trace.json"}
 
 
-def cpu_reference(w, seconds_budget=12.0, threads=None):
-    """the unmodified reference on the host cores: single-threaded and work_queue-threaded."""
+def cpu_reference(w, seconds_budget=12.0, threads=None, parity=None):
+    """THE cpu_baseline LEG -- the only place this arm touches oracle/: the unmodified reference on the host
+    cores (single-threaded and work_queue-threaded), the port's visit counters for the roofline numerator, and
+    a spot check of `parity` = (segments, gpu results) sampled from the timed run.  Runs after every timed region."""
     import oracle
+    extras = {}
+    port = oracle.Port(w["m"])
+    _, _, ctr = port.trace(host_segments(w, 0, 200_000), want_pos=False)
+    extras["counters"] = ctr
+    if parity is not None:
+        sseg, got = parity
+        exp, _, _ = port.trace(sseg, want_pos=False)
+        bad = int((got.view(np.uint32).reshape(-1, 4) != exp.view(np.uint32).reshape(-1, 4)).any(axis=1).sum())
+        extras["parity"] = {"checked": int(len(sseg)), "mismatches": bad}
     threads = threads or host_threads()
     kind = "reference" if oracle.have_reference() else "port"
     if kind == "reference":
@@ -218,14 +232,13 @@ def cpu_reference(w, seconds_budget=12.0, threads=None):
         for _ in range(3):                        # noisy -> warm up + best of k
             ref.trace(segs, threads=threads)
             best = max(best, nmt / ref.seconds)
-        return {"value": best, "unit": "traces/s", "cores": threads, "kind": kind,
+        return extras, {"value": best, "unit": "traces/s", "cores": threads, "kind": kind,
                 "single_thread": single,
                 "sample": f"{nmt} segments of this workload through BSP::trace_seg, reference work_queue with {threads - 1} workers + caller, "
                           f"best of 3; single-thread loop on {n1} segments = {single:.3e} traces/s"}
-    port = oracle.Port(w["m"])
     segs = host_segments(w, 0, 2_000_000)
     t0 = time.time(); port.trace(segs, want_pos=False); dt = time.time() - t0
-    return {"value": len(segs) / dt, "unit": "traces/s", "cores": 1, "kind": "port", "single_thread": len(segs) / dt,
+    return extras, {"value": len(segs) / dt, "unit": "traces/s", "cores": 1, "kind": "port", "single_thread": len(segs) / dt,
             "sample": f"{len(segs)} segments through oracle/restate.c, 1 thread (reference object not built on this box)"}
 
 
@@ -404,18 +417,11 @@ def run_ours(a):
 
     if rank == 0:
         clocks = sampler.stop() if sampler else None
-        # parity spot check of the gathered sample against the oracle (checker only, outside every timed region)
-        parity = None
-        try:
-            import oracle
-            sseg = sample_seg.cpu().numpy()
-            exp, _, _ = oracle.Port(w["m"]).trace(sseg, want_pos=False)
-            got = sample_res.cpu().numpy().view(np.uint32)
-            bad = int((got != exp.view(np.uint32).reshape(-1, 4)).any(axis=1).sum())
-            parity = {"checked": int(len(sseg)), "mismatches": bad}
-        except Exception as e:  # pragma: no cover
-            parity = {"error": str(e)}
-        bpt = algorithmic_bytes(w)
+        cpu_line, counters, parity = None, None, None
+        if world == 1 and not a.no_cpu:
+            extras, cpu_line = cpu_reference(w, parity=(sample_seg.cpu().numpy(), sample_res.cpu().numpy()))
+            counters, parity = extras.get("counters"), extras.get("parity")
+        bpt = algorithmic_bytes(w, counters)
         peak, peak_src = measured_peak()
         mean_kernel_ms = float(np.mean(kernel_ms))
         achieved = bpt["b_total"] * per_gpu / (mean_kernel_ms * 1e-3) / 1e9
@@ -440,7 +446,7 @@ def run_ours(a):
             "hits": total_hits, "parity_sample": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "bytes_per_trace": bpt["b_total"], "bytes_per_trace_map": bpt["b_map"],
-                         "bytes_per_trace_io": bpt["b_io"], "visit_means": bpt["means"], "kernel_ms": mean_kernel_ms,
+                         "bytes_per_trace_io": bpt["b_io"], "visit_means": bpt["means"], "visit_means_source": bpt["source"], "kernel_ms": mean_kernel_ms,
                          "hbm_stream_gbs": bpt["b_io"] * per_gpu / (mean_kernel_ms * 1e-3) / 1e9,
                          "note": "achieved = algorithmic bytes (map records the reference walk touches + 48 B segment/result I/O) per second; "
                                  "map bytes are served from shared memory / L1 / L2, only the I/O stream reaches HBM"},
@@ -450,8 +456,8 @@ def run_ours(a):
             "gpu_launches": launches_per_step * a.steps,
             "clocks": clocks,
         }
-        if world == 1 and not a.no_cpu:
-            line["cpu_baseline"] = cpu_reference(w)
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
         if world == 1 and a.also and a.also != a.workload:
             # the other single-GPU configuration of BASELINE.json (configs[1]: rooms8, 64 Mi uniform segments, map staged
             # in shared memory), device-resident, same timing rules -- reported beside the headline, not instead of it
@@ -493,7 +499,7 @@ def secondary_workload(name, a, local, stream):
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-    bpt = algorithmic_bytes(w2)
+    bpt = algorithmic_bytes(w2)          # committed visit counts
     peak, _ = measured_peak()
     info = g2.info()
     res = {"value": n2 / (ms * 1e-3), "unit": "traces/s", "ms_per_step": ms, "steps": steps, "segments_per_step": n2,
