@@ -448,6 +448,7 @@ def run_ours(a):
                          "peak_source": peak_src, "bytes_per_trace": bpt["b_total"], "bytes_per_trace_map": bpt["b_map"],
                          "bytes_per_trace_io": bpt["b_io"], "visit_means": bpt["means"], "visit_means_source": bpt["source"], "kernel_ms": mean_kernel_ms,
                          "hbm_stream_gbs": bpt["b_io"] * per_gpu / (mean_kernel_ms * 1e-3) / 1e9,
+                         "map_level": map_level_roofline(bpt, per_gpu / (mean_kernel_ms * 1e-3), info["variant"]),
                          "note": "achieved = algorithmic bytes (map records the reference walk touches + 48 B segment/result I/O) per second; "
                                  "map bytes are served from shared memory / L1 / L2, only the I/O stream reaches HBM"},
             "e2e": {"value": e2e_value, "unit": "traces/s", "h2d_bytes_per_step": e2e_n * 24, "d2h_bytes_per_step": e2e_n * 16,
@@ -475,6 +476,25 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def map_level_roofline(bpt, traces_per_s, variant):
+    """the level that actually holds the map: record gathers per second against the measured scattered-gather
+    rate of that level (profiles/r1_microbench.json, tools/microbench) -- the binding resource of this kernel."""
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "profiles", "r1_microbench.json")))
+        m = bpt["means"]
+        gathers = m["nodes"] + m["sides"] + m["leaf_brushes"]           # node records, side planes, brush references
+        in_smem = variant == 1
+        peak = peaks["peaks_used_by_bench"]["smem_chase_gathers_per_s" if in_smem else "global_gathers_per_s"]
+        return {"level": "shared memory" if in_smem else "L1/L2 read-only path", "record_gathers_per_trace": gathers,
+                "achieved_gathers_per_s": gathers * traces_per_s, "peak_gathers_per_s": peak, "frac": gathers * traces_per_s / peak,
+                "map_bytes_gbs": bpt["b_map"] * traces_per_s / 1e9,
+                "level_bandwidth_gbs": peaks["smem_read_gbs" if in_smem else "l2_read_gbs"],
+                "note": "peak = fully scattered 32-byte gathers (every lane a different record); the trace's top-of-tree gathers are "
+                        "shared between lanes, so frac can exceed 1"}
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)}
 
 
 def secondary_workload(name, a, local, stream):
