@@ -67,6 +67,21 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             raise RuntimeError("g++ failed building libbsphost.so")
 
 
+def build_microbench(force: bool = False, verbose: bool = False) -> str:
+    """tools/microbench/microbench: measures the L2 / shared-memory / scattered-gather peaks on the box."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tools", "microbench", "microbench.cu")
+    exe = os.path.join(root, "tools", "microbench", "microbench")
+    if force or _stale(exe, [src]):
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o", exe, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            print(" ".join(cmd)); print(r.stdout); print(r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed building tools/microbench")
+    return exe
+
+
 if __name__ == "__main__":
     import sys
     build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv)
