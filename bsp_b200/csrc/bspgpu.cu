@@ -329,6 +329,9 @@ int bspgpu_trace_pos( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result
 	const bool segs_dev = ( flags & BSPGPU_SEGS_DEVICE ) != 0, out_dev = ( flags & BSPGPU_OUT_DEVICE ) != 0;
 	const bool packed = ( flags & BSPGPU_SEGS_PACKED24 ) != 0;
 	if( ( flags & BSPGPU_ASYNC ) && !( segs_dev && out_dev ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: BSPGPU_ASYNC needs device pointers" );
+	/* the kernels read segments with 128-bit (packed: 64-bit) loads and write 16-byte records */
+	if( segs_dev && ( ( uintptr_t ) segs % ( packed ? 8 : 16 ) ) != 0 ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: device segments must be 16-byte aligned (8-byte for the packed layout)" );
+	if( out_dev && ( ( ( uintptr_t ) out % 16 ) != 0 || ( ( uintptr_t ) pos % 16 ) != 0 ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: device results must be 16-byte aligned" );
 	CK( cudaSetDevice( h->device ) );
 	cudaStream_t st = h->stream();
 	h->last_launches = 0;

@@ -85,8 +85,8 @@ typedef struct bspgpu_result {
 typedef struct bspgpu_pos { float pos[ 3 ]; float t; } bspgpu_pos;
 
 /* bspgpu_trace flags */
-#define BSPGPU_SEGS_DEVICE   0x01u  /* segs is a device pointer (already resident in HBM) */
-#define BSPGPU_OUT_DEVICE    0x02u  /* out / pos are device pointers */
+#define BSPGPU_SEGS_DEVICE   0x01u  /* segs is a device pointer (already resident in HBM), 16-byte aligned (8 if packed) */
+#define BSPGPU_OUT_DEVICE    0x02u  /* out / pos are device pointers, 16-byte aligned */
 #define BSPGPU_SEGS_PACKED24 0x04u  /* segs are 6 floats each (two glm::vec3, the reference's own argument layout) */
 #define BSPGPU_ASYNC         0x08u  /* device pointers only: enqueue on the handle's stream and return */
 
