@@ -97,6 +97,7 @@ struct bspgpu {
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 96 * 1024;
 	int64_t opt_chunk = 2ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;   /* 0 = per-variant default */
 	int64_t opt_sched = 0, opt_side_steps = 8, opt_leaf_threshold = 16;
+	int64_t opt_start_grid = -1;   /* -1 auto: on unless the whole map sits in shared memory (there a node step is cheaper than the grid's global load) */
 	uint64_t opt_max_launch = kMaxLaunchSegs;   /* segments per kernel launch (lowered by tests to exercise the multi-launch path) */
 
 	/* launch configuration, recomputed only after an option changed */
@@ -180,6 +181,9 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 	p.side_steps = ( uint32_t ) ( h->opt_side_steps < 1 ? 1 : h->opt_side_steps );
 	p.leaf_threshold = ( uint32_t ) ( h->opt_leaf_threshold < 1 ? 1 : ( h->opt_leaf_threshold > 32 ? 32 : h->opt_leaf_threshold ) );
 	p.hits = h->d_counters;
+	p.grid.d = h->lay.grid;
+	const bool use_grid = h->opt_start_grid < 0 ? mode != kSmemAll : h->opt_start_grid != 0;
+	p.grid.cells = ( use_grid && h->opt_sched != 3 && h->lay.grid.dim[ 0 ] ) ? reinterpret_cast< const int32_t * >( h->d_image + h->lay.off_grid ) : nullptr;
 
 	h->last_variant = ( uint32_t ) variant; h->last_threads = ( uint32_t ) threads; h->last_grid = ( uint32_t ) grid; h->last_smem = smem;
 
@@ -497,6 +501,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 		case BSPGPU_OPT_SCHEDULER: h->opt_sched = value; break;
 		case BSPGPU_OPT_SIDE_STEPS: h->opt_side_steps = value; break;
 		case BSPGPU_OPT_LEAF_THRESHOLD: h->opt_leaf_threshold = value; break;
+		case BSPGPU_OPT_START_GRID: h->opt_start_grid = value < 0 ? -1 : ( value ? 1 : 0 ); break;
 		case BSPGPU_OPT_MAX_LAUNCH_SEGMENTS:
 			if( value < 32 || ( uint64_t ) value > kMaxLaunchSegs ) return fail( BSPGPU_E_INVALID, "max launch segments must be in [32, 2^30]" );
 			h->opt_max_launch = ( uint64_t ) value; break;
@@ -539,6 +544,8 @@ int bspgpu_get_info( bspgpu_t * h, bspgpu_info * info ) {
 	info->smem_bytes = h->last_smem; info->tree_depth = h->lay.tree_depth;
 	info->num_nodes = h->lay.num_nodes; info->num_brush_refs = h->lay.num_refs; info->num_sides = h->lay.num_sides;
 	info->map_bytes = h->lay.total_bytes; info->last_launches = h->last_launches;
+	info->staged_bytes = ( uint32_t ) h->lay.staged_bytes;
+	info->start_grid_cells = ( uint32_t ) ( ( uint64_t ) h->lay.grid.dim[ 0 ] * h->lay.grid.dim[ 1 ] * h->lay.grid.dim[ 2 ] );
 	if( h->timing_valid ) {
 		CK( cudaSetDevice( h->device ) );
 		CK( cudaEventSynchronize( h->ev_stop ) );

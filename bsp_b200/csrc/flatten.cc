@@ -10,8 +10,11 @@
  */
 #include "flatten.h"
 
+#include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <cmath>
 
 namespace bspk {
 
@@ -151,7 +154,84 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	lay.off_sides = align_up( lay.off_refs + ( uint64_t ) orefs.size() * sizeof( BrushRef ), kSectionAlign );
 	lay.staged_bytes = align_up( lay.off_sides + ( uint64_t ) num_sides_out * sizeof( SideRec ), kSectionAlign );
 	lay.off_side_plane = lay.staged_bytes;
-	lay.total_bytes = align_up( lay.off_side_plane + ( uint64_t ) num_sides_out * sizeof( uint32_t ), kSectionAlign );
+	lay.off_grid = align_up( lay.off_side_plane + ( uint64_t ) num_sides_out * sizeof( uint32_t ), kSectionAlign );
+
+	/* ---- start grid (map_layout.h).  World box = the root node's bounds (reference bsp.h:63-64 mins/maxs, unused
+	 *      by the reference's trace); no grid when a map does not carry them. */
+	std::vector< int32_t > grid_cells;
+	memset( &lay.grid, 0, sizeof( lay.grid ) );
+	{
+		const DiskNode & root = nodes[ 0 ];
+		double ext[ 3 ], wlo[ 3 ];
+		bool ok = true;
+		double scale = 1.0;
+		for( int a = 0; a < 3; a++ ) {
+			wlo[ a ] = root.mins[ a ]; ext[ a ] = ( double ) root.maxs[ a ] - root.mins[ a ];
+			ok = ok && ext[ a ] >= 1.0 && ext[ a ] < 1e7;
+			if( fabs( ( double ) root.mins[ a ] ) > scale ) scale = fabs( ( double ) root.mins[ a ] );
+			if( fabs( ( double ) root.maxs[ a ] ) > scale ) scale = fabs( ( double ) root.maxs[ a ] );
+		}
+		for( uint32_t i = 0; ok && i < num_nodes; i++ ) {
+			const NodeRec & n = onodes[ i ];
+			ok = ok && std::isfinite( n.nx ) && std::isfinite( n.ny ) && std::isfinite( n.nz ) && std::isfinite( n.d );
+			const double nlen = fabs( ( double ) n.nx ) + fabs( ( double ) n.ny ) + fabs( ( double ) n.nz );
+			ok = ok && nlen < 4.0;                       /* the margins below assume roughly unit normals */
+			if( fabs( ( double ) n.d ) > scale ) scale = fabs( ( double ) n.d );
+		}
+		if( ok ) {
+			/* ~cubic cells, about 2^20 of them (4 MB), at most 256 along an axis */
+			double target_cells = 1048576.0;
+			if( const char * env = getenv( "BSPGPU_GRID_CELLS" ) ) { const double v = atof( env ); if( v >= 1.0 && v <= 6.4e7 ) target_cells = v; }   /* tuning knob */
+			double cell = cbrt( ext[ 0 ] * ext[ 1 ] * ext[ 2 ] / target_cells );
+			int32_t dim[ 3 ];
+			for( int pass = 0; pass < 2; pass++ ) {
+				for( int a = 0; a < 3; a++ ) {
+					dim[ a ] = ( int32_t ) ceil( ext[ a ] / cell );
+					if( dim[ a ] < 1 ) dim[ a ] = 1;
+					if( dim[ a ] > 1024 ) dim[ a ] = 1024;
+				}
+				if( ( double ) dim[ 0 ] * dim[ 1 ] * dim[ 2 ] <= 1.15 * target_cells ) break;
+				cell *= 1.3;
+			}
+			/* margins: fp32 evaluation of dot(p,n)-d is off by < 2^-20*scale, the crossing parameter by a relative
+			 * 2^-22; delta leaves a 20x reserve.  pad covers the rounding of the kernel's cell index. */
+			const double delta = 0.25 + scale / 32768.0;
+			const double pad = 0.25 + scale / 65536.0;
+			grid_cells.resize( ( size_t ) dim[ 0 ] * dim[ 1 ] * dim[ 2 ] );
+			for( int32_t iz = 0; iz < dim[ 2 ]; iz++ ) for( int32_t iy = 0; iy < dim[ 1 ]; iy++ ) for( int32_t ix = 0; ix < dim[ 0 ]; ix++ ) {
+				const int32_t ic[ 3 ] = { ix, iy, iz };
+				double blo[ 3 ], bhi[ 3 ];
+				for( int a = 0; a < 3; a++ ) {
+					const double cs = ext[ a ] / dim[ a ];
+					blo[ a ] = wlo[ a ] + ic[ a ] * cs - pad; bhi[ a ] = wlo[ a ] + ( ic[ a ] + 1 ) * cs + pad;
+				}
+				int32_t ref = 0;
+				for( ;; ) {
+					const NodeRec & n = onodes[ ref ];
+					const double nn[ 3 ] = { n.nx, n.ny, n.nz };
+					double dmin = -( double ) n.d, dmax = -( double ) n.d;
+					for( int a = 0; a < 3; a++ ) {
+						dmin += nn[ a ] >= 0.0 ? nn[ a ] * blo[ a ] : nn[ a ] * bhi[ a ];
+						dmax += nn[ a ] >= 0.0 ? nn[ a ] * bhi[ a ] : nn[ a ] * blo[ a ];
+					}
+					int32_t child;
+					if( dmin >= delta ) child = n.child[ 0 ];          /* everything in front: children[ dist > 0 ] = children[ 0 ] */
+					else if( dmax <= -delta ) child = n.child[ 1 ];
+					else break;
+					ref = child;
+					if( child < 0 ) break;                          /* a leaf reference or kEmptyLeaf */
+				}
+				grid_cells[ ( ( size_t ) iz * dim[ 1 ] + iy ) * dim[ 0 ] + ix ] = ref;
+			}
+			for( int a = 0; a < 3; a++ ) {
+				lay.grid.dim[ a ] = dim[ a ];
+				lay.grid.lo[ a ] = ( float ) wlo[ a ];
+				lay.grid.hi[ a ] = ( float ) ( wlo[ a ] + ext[ a ] );
+				lay.grid.inv[ a ] = ( float ) ( dim[ a ] / ext[ a ] );
+			}
+		}
+	}
+	lay.total_bytes = align_up( lay.off_grid + ( uint64_t ) grid_cells.size() * sizeof( int32_t ), kSectionAlign );
 	if( lay.total_bytes == 0 ) lay.total_bytes = kSectionAlign;
 
 	out.image.assign( lay.total_bytes, 0 );
@@ -166,6 +246,7 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	}
 	osides[ L.num_brush_sides ].nx = osides[ L.num_brush_sides ].ny = osides[ L.num_brush_sides ].nz = osides[ L.num_brush_sides ].d = 0.0f;
 	oside_plane[ L.num_brush_sides ] = 0;
+	if( !grid_cells.empty() ) memcpy( out.image.data() + lay.off_grid, grid_cells.data(), grid_cells.size() * sizeof( int32_t ) );
 	return BSPGPU_OK;
 }
 

@@ -48,11 +48,23 @@ static const int32_t kEmptyLeaf = INT32_MIN;
 static const uint32_t kLastRef = 0x80000000u;
 static const uint32_t kSectionAlign = 128;
 
+/* Start grid: a uniform grid over the world box; cell -> the deepest child reference such that every
+ * ancestor's plane has the whole (padded) cell at least `delta` away on one side.  A segment with both
+ * endpoints in one cell is a pass-through at all those ancestors in the reference (bsp.cc:226-237: the
+ * crossing parameter is provably < 0 or > 1, so only the near child is visited, interval unchanged), so the
+ * walk may start at that reference instead of node 0 and still be bit-identical.  See flatten.cc. */
+struct StartGridDesc {
+	int32_t dim[ 3 ];        /* 0 = no grid */
+	float lo[ 3 ], hi[ 3 ];  /* points must satisfy lo <= p < hi (false for NaN) */
+	float inv[ 3 ];          /* cells per unit */
+};
+
 /* byte offsets of the sections inside the single device image */
 struct MapImageLayout {
 	uint32_t num_nodes, num_refs, num_sides, tree_depth;
-	uint64_t off_nodes, off_refs, off_sides, off_side_plane, total_bytes;
+	uint64_t off_nodes, off_refs, off_sides, off_side_plane, off_grid, total_bytes;
 	uint64_t staged_bytes;   /* prefix [nodes|refs|sides] the whole-map variant copies to shared memory */
+	StartGridDesc grid;
 };
 
 } // namespace bspk

@@ -252,6 +252,37 @@ BSPK_HD void lane_start( Lane & l, float sx, float sy, float sz, float ex, float
 	l.ht = 1.0f; l.hflags = 0; l.hside = -1; l.hbrush = -1;      /* bsp.cc:256-257 */
 	l.tmin = 0.0f; l.tmax = 1.0f; l.cur = 0; l.sp = 0;          /* bsp.cc:263 */
 	l.s = 0; l.s_end = 0;
+	l.brush = -1; l.bflags = 0; l.tfar = 0.0f; l.tnear = 0.0f; l.far_side = -1;
+}
+
+struct StartGrid {
+	const int32_t * cells;   /* null = disabled */
+	StartGridDesc d;
+};
+
+/* where the walk of segment (s, e) may start: node 0 (bsp.cc:263), or -- when both endpoints lie in the same
+ * start-grid cell -- the child reference stored for that cell (map_layout.h).  Comparisons are written so
+ * that NaN / infinite coordinates fall back to node 0. */
+BSPK_HD int32_t grid_start_ref( const StartGrid & g, float sx, float sy, float sz, float ex, float ey, float ez ) {
+	if( !g.cells ) return 0;
+	const StartGridDesc & d = g.d;
+	/* cheap way out for segments longer than a cell (this is only a filter: the decision is the cell test below) */
+	if( !( ( ex - sx ) * d.inv[ 0 ] < 1.0f && ( sx - ex ) * d.inv[ 0 ] < 1.0f && ( ey - sy ) * d.inv[ 1 ] < 1.0f && ( sy - ey ) * d.inv[ 1 ] < 1.0f
+	    && ( ez - sz ) * d.inv[ 2 ] < 1.0f && ( sz - ez ) * d.inv[ 2 ] < 1.0f ) ) return 0;
+	const bool inside = sx >= d.lo[ 0 ] && sx < d.hi[ 0 ] && sy >= d.lo[ 1 ] && sy < d.hi[ 1 ] && sz >= d.lo[ 2 ] && sz < d.hi[ 2 ]
+	                 && ex >= d.lo[ 0 ] && ex < d.hi[ 0 ] && ey >= d.lo[ 1 ] && ey < d.hi[ 1 ] && ez >= d.lo[ 2 ] && ez < d.hi[ 2 ];
+	if( !inside ) return 0;
+	int32_t ix = ( int32_t ) ( ( sx - d.lo[ 0 ] ) * d.inv[ 0 ] ), iy = ( int32_t ) ( ( sy - d.lo[ 1 ] ) * d.inv[ 1 ] ), iz = ( int32_t ) ( ( sz - d.lo[ 2 ] ) * d.inv[ 2 ] );
+	int32_t jx = ( int32_t ) ( ( ex - d.lo[ 0 ] ) * d.inv[ 0 ] ), jy = ( int32_t ) ( ( ey - d.lo[ 1 ] ) * d.inv[ 1 ] ), jz = ( int32_t ) ( ( ez - d.lo[ 2 ] ) * d.inv[ 2 ] );
+	ix = ix < d.dim[ 0 ] ? ix : d.dim[ 0 ] - 1; iy = iy < d.dim[ 1 ] ? iy : d.dim[ 1 ] - 1; iz = iz < d.dim[ 2 ] ? iz : d.dim[ 2 ] - 1;
+	jx = jx < d.dim[ 0 ] ? jx : d.dim[ 0 ] - 1; jy = jy < d.dim[ 1 ] ? jy : d.dim[ 1 ] - 1; jz = jz < d.dim[ 2 ] ? jz : d.dim[ 2 ] - 1;
+	if( ix != jx || iy != jy || iz != jz ) return 0;
+	return g.cells[ ( ( int64_t ) iz * d.dim[ 1 ] + iy ) * d.dim[ 0 ] + ix ];
+}
+
+/* begin the walk at a start reference from grid_start_ref (0 = the root) */
+BSPK_HD void lane_start_at( Lane & l, int32_t ref ) {
+	l.cur = ref == kEmptyLeaf ? kCurDone : ref;   /* the whole segment lies in a leaf without solid brushes: a miss, t = 1 */
 }
 
 BSPK_HD void lane_hit_state( const Lane & l, HitState & h ) {
@@ -364,10 +395,11 @@ BSPK_HD void lane_leaf_phase( const Map & map, Lane & l, const StackEntry16 * st
 /* trace_one written with the resumable phases (budgets make no difference to the result) */
 template< class Map, int kStack >
 BSPK_HD void trace_one_phased( const Map & map, float sx, float sy, float sz, float ex, float ey, float ez,
-                               uint32_t node_budget, uint32_t side_budget, Ray & r_out, HitState & h_out ) {
+                               uint32_t node_budget, uint32_t side_budget, Ray & r_out, HitState & h_out, const StartGrid * grid = nullptr ) {
 	StackEntry16 stack[ kStack ];
 	Lane l;
 	lane_start( l, sx, sy, sz, ex, ey, ez );
+	if( grid ) lane_start_at( l, grid_start_ref( *grid, sx, sy, sz, ex, ey, ez ) );
 	while( !lane_done( l ) ) {
 		lane_node_phase( map, l, stack, node_budget );
 		lane_leaf_phase( map, l, stack, side_budget );

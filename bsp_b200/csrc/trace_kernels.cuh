@@ -53,6 +53,7 @@ struct TraceParams {
 	uint32_t max_steps;               /* node steps per lane per node phase (bounds divergence) */
 	uint32_t side_steps;              /* side steps per lane per leaf phase */
 	uint32_t leaf_threshold;          /* lanes waiting in a leaf that make the warp run a leaf phase */
+	StartGrid grid;                   /* cells == null: every walk starts at node 0 */
 	unsigned long long * next;        /* work counter, zeroed before launch */
 	unsigned long long * hits;        /* accumulated hit count */
 };
@@ -349,6 +350,23 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TracePa
 	if( lane == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
 }
 
+/* read segment `sidx`, begin its walk: at node 0 (bsp.cc:263) or at the start-grid reference of its cell */
+__device__ __forceinline__ void lane_load_segment( const TraceParams & p, uint32_t sidx, Lane & l ) {
+	float sx, sy, sz, ex, ey, ez;
+	if( p.segs24 ) {
+		const float2 * sp24 = p.segs24 + ( size_t ) sidx * 3;
+		const float2 a = ld_stream2( sp24 ), b2 = ld_stream2( sp24 + 1 ), c = ld_stream2( sp24 + 2 );
+		sx = a.x; sy = a.y; sz = b2.x; ex = b2.y; ey = c.x; ez = c.y;
+	}
+	else {
+		const float4 a = ld_stream4( p.segs + ( size_t ) sidx * 2 );
+		const float4 b4 = ld_stream4( p.segs + ( size_t ) sidx * 2 + 1 );
+		sx = a.x; sy = a.y; sz = a.z; ex = b4.x; ey = b4.y; ez = b4.z;
+	}
+	lane_start( l, sx, sy, sz, ex, ey, ez );
+	if( p.grid.cells ) lane_start_at( l, grid_start_ref( p.grid, sx, sy, sz, ex, ey, ez ) );
+}
+
 /* ---------------------------------------------------------------- K1/K2, phase-scheduled
  *
  * ncu on the round-based kernel above showed it issue-bound (88 % issue-active on rooms8) at
@@ -415,6 +433,21 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 	uint32_t seg = 0, my_hits = 0;
 
 	for( ;; ) {
+		/* ---- retire finished segments (also those the start grid resolved at load time: a segment inside an empty leaf) */
+		if( lane_done( l ) ) {
+			HitState h;
+			lane_hit_state( l, h );
+			const ResultRec o = make_result( h, side_plane );
+			if( p.out ) st_stream4( p.out + seg, o.t, __int_as_float( o.plane ), __int_as_float( o.brush ), __uint_as_float( o.flags ) );
+			if( p.pos ) {
+				float px, py, pz;
+				make_pos( l.r, h, px, py, pz );                                 /* bsp.cc:265-267 */
+				st_stream4( p.pos + seg, px, py, pz, h.t );
+			}
+			my_hits += ( uint32_t ) h.hit;
+			l.cur = kCurIdle;
+		}
+
 		/* ---- warp-level work fetch + compaction */
 		const unsigned idle = __ballot_sync( kFull, lane_idle( l ) );
 		const unsigned n_idle = __popc( idle );
@@ -434,16 +467,7 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 				const uint32_t rank = __popc( idle & lt_mask );
 				if( lane_idle( l ) && rank < avail ) {
 					seg = blk_next + rank;
-					if( p.segs24 ) {
-						const float2 * sp24 = p.segs24 + ( size_t ) seg * 3;
-						const float2 a = ld_stream2( sp24 ), b2 = ld_stream2( sp24 + 1 ), c = ld_stream2( sp24 + 2 );
-						lane_start( l, a.x, a.y, b2.x, b2.y, c.x, c.y );
-					}
-					else {
-						const float4 a = ld_stream4( p.segs + ( size_t ) seg * 2 );
-						const float4 b4 = ld_stream4( p.segs + ( size_t ) seg * 2 + 1 );
-						lane_start( l, a.x, a.y, a.z, b4.x, b4.y, b4.z );
-					}
+					lane_load_segment( p, seg, l );
 				}
 				blk_next += min( n_idle, avail );
 			}
@@ -453,26 +477,13 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 		const unsigned in_node = __ballot_sync( kFull, lane_in_node( l ) );
 		const unsigned in_leaf = __ballot_sync( kFull, lane_in_leaf( l ) );
 		if( ( in_node | in_leaf ) == 0u ) {
+			if( __ballot_sync( kFull, lane_done( l ) ) != 0u ) continue;       /* loaded and already finished: retire them first */
 			if( !more_work ) break;
 			continue;
 		}
 		if( in_node == 0u || ( uint32_t ) __popc( in_leaf ) >= p.leaf_threshold ) lane_leaf_phase( map, l, stack, p.side_steps );
 		else lane_node_phase( map, l, stack, p.max_steps );
 
-		/* ---- retire finished segments */
-		if( lane_done( l ) ) {
-			HitState h;
-			lane_hit_state( l, h );
-			const ResultRec o = make_result( h, side_plane );
-			if( p.out ) st_stream4( p.out + seg, o.t, __int_as_float( o.plane ), __int_as_float( o.brush ), __uint_as_float( o.flags ) );
-			if( p.pos ) {
-				float px, py, pz;
-				make_pos( l.r, h, px, py, pz );                                 /* bsp.cc:265-267 */
-				st_stream4( p.pos + seg, px, py, pz, h.t );
-			}
-			my_hits += ( uint32_t ) h.hit;
-			l.cur = kCurIdle;
-		}
 	}
 
 	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( kFull, my_hits, o );
@@ -526,19 +537,6 @@ __device__ __forceinline__ void lane_swap( const ParkSlot & slot, Lane & l, uint
 	l.hside = __float_as_int( f_hside ); l.hbrush = __float_as_int( f_hbrush ); l.s = __float_as_uint( f_s );
 	l.s_end = __float_as_uint( f_send ); l.brush = __float_as_int( f_brush ); l.bflags = __float_as_uint( f_bflags );
 	l.far_side = __float_as_int( f_fside ); seg = __float_as_uint( f_seg );
-}
-
-__device__ __forceinline__ void lane_load_segment( const TraceParams & p, uint32_t sidx, Lane & l ) {
-	if( p.segs24 ) {
-		const float2 * sp24 = p.segs24 + ( size_t ) sidx * 3;
-		const float2 a = ld_stream2( sp24 ), b2 = ld_stream2( sp24 + 1 ), c = ld_stream2( sp24 + 2 );
-		lane_start( l, a.x, a.y, b2.x, b2.y, c.x, c.y );
-	}
-	else {
-		const float4 a = ld_stream4( p.segs + ( size_t ) sidx * 2 );
-		const float4 b4 = ld_stream4( p.segs + ( size_t ) sidx * 2 + 1 );
-		lane_start( l, a.x, a.y, a.z, b4.x, b4.y, b4.z );
-	}
 }
 
 template< int kMode, int kStack, int kMaxThreads >

@@ -110,7 +110,9 @@ enum {
 	                                   2 = phase-scheduled at <= 40 registers (1536 threads/SM), 3 = two segments per lane (experimental) */
 	BSPGPU_OPT_SIDE_STEPS = 10,     /* brush-side steps a lane takes per leaf phase */
 	BSPGPU_OPT_LEAF_THRESHOLD = 11, /* lanes waiting in a leaf that make a warp run a leaf phase (1..32) */
-	BSPGPU_OPT_MAX_LAUNCH_SEGMENTS = 12 /* segments per kernel launch, default and maximum 2^30 (in-kernel indices are 32-bit) */
+	BSPGPU_OPT_MAX_LAUNCH_SEGMENTS = 12, /* segments per kernel launch, default and maximum 2^30 (in-kernel indices are 32-bit) */
+	BSPGPU_OPT_START_GRID = 13      /* segments whose endpoints share a start-grid cell begin below the root (bit-identical, see map_layout.h):
+	                                   1 on, 0 off (always node 0), -1 (default) on unless the map is staged in shared memory */
 };
 
 typedef struct bspgpu_info {
@@ -125,6 +127,8 @@ typedef struct bspgpu_info {
 	uint64_t map_bytes;          /* flattened device image size */
 	float last_kernel_ms;        /* CUDA-event time of the last trace's kernel(s) on the handle's stream */
 	uint32_t last_launches;      /* kernels launched by the last call */
+	uint32_t start_grid_cells;   /* 0 when the map carries no world bounds (root node mins/maxs) */
+	uint32_t staged_bytes;       /* size of [nodes|refs|sides]: what the SMEM variant needs in shared memory */
 } bspgpu_info;
 
 /* ---- lifetime (replaces nothing: the reference keeps the map in host memory; this COPIES and

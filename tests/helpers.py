@@ -32,6 +32,38 @@ def mixed_segments(m, n_uniform=200_000, n_long=200_000, n_short=100_000, n_edge
     ))
 
 
+def grid_adversarial_segments(m, n, seed=5):
+    """segments built to break the start grid if its margins were wrong: endpoints on / a few ulps or a
+    fraction of a unit beside start-grid cell borders, lengths from 0 to a few cells, and a third of them
+    hugging axial node planes on either side."""
+    rs = np.random.Generator(np.random.PCG64(seed))
+    lo = np.array(m.nodes["mins"][0], np.float64); hi = np.array(m.nodes["maxs"][0], np.float64)
+    ext = hi - lo
+    assert (ext > 0).all(), "map has no world bounds in its root node"
+    cell = np.cbrt(ext.prod() / 1048576.0)
+    dim = np.clip(np.ceil(ext / cell), 1, 256)
+    cs = ext / dim
+    p = lo + ext * rs.random((n, 3))
+    ax = rs.integers(0, 3, n)
+    k = np.round((p[np.arange(n), ax] - lo[ax]) / cs[ax])
+    p[np.arange(n), ax] = lo[ax] + k * cs[ax] + rs.choice([0.0, 1e-3, -1e-3, 1e-5, -1e-5, 0.4, -0.4], n)
+    d = rs.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+    e = p + d * rs.choice([0.0, 1e-3, 0.5, 4.0, 30.0, 200.0], n)[:, None]
+    segs = np.zeros((n, 8), np.float32)
+    segs[:, 0:3] = p; segs[:, 4:7] = e
+    planes = m.planes[m.nodes["plane"]]
+    axial = np.nonzero((np.abs(planes["n"]) == 1.0).any(axis=1))[0]
+    if len(axial):
+        cnt = n // 3
+        sel = rs.choice(axial, cnt)
+        a = np.argmax(np.abs(planes["n"][sel]), axis=1)
+        val = planes["d"][sel] * planes["n"][sel][np.arange(cnt), a]
+        off = [0.0, 1e-3, -1e-3, 0.3, -0.3, 1.1, -1.1]
+        segs[np.arange(cnt), a] = (val + rs.choice(off, cnt)).astype(np.float32)
+        segs[np.arange(cnt), 4 + a] = (val + rs.choice(off, cnt)).astype(np.float32)
+    return segs
+
+
 class HostSim:
     """tests/hostsim: a g++ build of bsp_b200/csrc/trace_core.h + flatten.cc (test-only)."""
 
@@ -52,7 +84,7 @@ class HostSim:
             lib.hostsim_destroy.argtypes = [C.c_void_p]
             lib.hostsim_layout.argtypes = [C.c_void_p, C.c_void_p]
             lib.hostsim_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
-            lib.hostsim_trace_phased.argtypes = lib.hostsim_trace.argtypes + [C.c_uint32, C.c_uint32]
+            lib.hostsim_trace_phased.argtypes = lib.hostsim_trace.argtypes + [C.c_uint32, C.c_uint32, C.c_int]
             lib.hostsim_leaf.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
             cls._lib = lib
         return cls._lib
@@ -72,11 +104,11 @@ class HostSim:
             raise ValueError(self.l.hostsim_error().decode())
 
     def layout(self):
-        out = np.zeros(6, np.uint64)
+        out = np.zeros(7, np.uint64)
         self.l.hostsim_layout(self.h, out.ctypes.data)
-        return dict(zip(("nodes", "refs", "sides", "depth", "staged_bytes", "total_bytes"), (int(v) for v in out)))
+        return dict(zip(("nodes", "refs", "sides", "depth", "staged_bytes", "total_bytes", "grid_cells"), (int(v) for v in out)))
 
-    def trace(self, segs, budgets=None):
+    def trace(self, segs, budgets=None, grid=False):
         from bsp_b200.api import RESULT_DT
         segs = np.ascontiguousarray(segs, np.float32)
         res = np.zeros(len(segs), RESULT_DT)
@@ -84,7 +116,7 @@ class HostSim:
         if budgets is None:
             self.l.hostsim_trace(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data)
         else:
-            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1])
+            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], 1 if grid else 0)
         return res, pos
 
     def leaf(self, pts):

@@ -22,6 +22,7 @@ struct Sim {
 	FlatMap flat;
 	ImageMap view;
 	const uint32_t * side_plane;
+	StartGrid grid;
 };
 std::string g_err;
 }
@@ -36,6 +37,8 @@ void * hostsim_create( const bspgpu_map_desc * lumps ) {
 	s->view.refs = ( const BrushRef * ) ( img + s->flat.layout.off_refs );
 	s->view.sides = ( const SideRec * ) ( img + s->flat.layout.off_sides );
 	s->side_plane = ( const uint32_t * ) ( img + s->flat.layout.off_side_plane );
+	s->grid.d = s->flat.layout.grid;
+	s->grid.cells = s->flat.layout.grid.dim[ 0 ] ? ( const int32_t * ) ( img + s->flat.layout.off_grid ) : nullptr;
 	return s;
 }
 
@@ -47,6 +50,7 @@ void hostsim_layout( void * h, uint64_t * out ) {
 	const MapImageLayout & l = ( ( Sim * ) h )->flat.layout;
 	out[ 0 ] = l.num_nodes; out[ 1 ] = l.num_refs; out[ 2 ] = l.num_sides; out[ 3 ] = l.tree_depth;
 	out[ 4 ] = l.staged_bytes; out[ 5 ] = l.total_bytes;
+	out[ 6 ] = ( uint64_t ) l.grid.dim[ 0 ] * l.grid.dim[ 1 ] * l.grid.dim[ 2 ];
 }
 
 /* segs: `stride` floats per segment, end point `end_off` floats after the start point */
@@ -71,7 +75,7 @@ void hostsim_trace( void * h, const float * segs, uint64_t stride, uint64_t end_
 /* same walk through the resumable node/leaf phases the persistent kernel runs, with small and
  * varying step budgets so every suspend/resume point is exercised */
 void hostsim_trace_phased( void * h, const float * segs, uint64_t stride, uint64_t end_off, uint64_t n, ResultRec * out, float * pos4,
-                           uint32_t node_budget, uint32_t side_budget ) {
+                           uint32_t node_budget, uint32_t side_budget, int use_grid ) {
 	const Sim * s = ( const Sim * ) h;
 	for( uint64_t i = 0; i < n; i++ ) {
 		const float * a = segs + i * stride;
@@ -79,7 +83,7 @@ void hostsim_trace_phased( void * h, const float * segs, uint64_t stride, uint64
 		Ray r; HitState hs;
 		const uint32_t nb = node_budget ? node_budget : 1 + ( uint32_t ) ( i % 7 );
 		const uint32_t sb = side_budget ? side_budget : 1 + ( uint32_t ) ( ( i / 7 ) % 5 );
-		trace_one_phased< ImageMap, 64 >( s->view, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs );
+		trace_one_phased< ImageMap, 64 >( s->view, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, use_grid ? &s->grid : nullptr );
 		if( out ) out[ i ] = make_result( hs, s->side_plane );
 		if( pos4 ) {
 			make_pos( r, hs, pos4[ 4 * i + 0 ], pos4[ 4 * i + 1 ], pos4[ 4 * i + 2 ] );

@@ -65,7 +65,7 @@ def test_kat_vectors(native, maps):
 def test_parity_vs_oracle(native, maps, oracle_mod, mapname, variant):
     m, path = maps(mapname)
     g = native.BspGpu(m)
-    if variant == "smem" and g.info()["map_bytes"] > 200 * 1024:
+    if variant == "smem" and g.info()["staged_bytes"] > 200 * 1024:
         with pytest.raises(native.BspGpuError):
             g.set_option(1, VARIANTS[variant]); g.trace(np.zeros((1, 8), np.float32))
         return
@@ -188,7 +188,7 @@ def test_full_size_properties(native, maps, oracle_mod, mapname, kind, n):
         g.generate(segs, first, n, 0, 2, lo, hi)
     else:
         g.generate(segs, first, n, 1, 3, lo, hi, 0.25 * diag, diag)
-    fits_smem = g.info()["map_bytes"] < 200 * 1024
+    fits_smem = g.info()["staged_bytes"] < 200 * 1024
     configs = [(0, 0)] + ([(2, 0)] if fits_smem else []) + [(3, 0), (0, 1)]       # (variant, scheduler)
     ref_out, ref_hits = None, None
     for variant, sched in configs:
@@ -426,4 +426,26 @@ def test_mixed_pointer_kinds_and_pos_only(native, maps, oracle_mod):
     assert np.array_equal(bits(pos[:, :3]), bits(exp_pos)) and np.array_equal(bits(pos[:, 3]), bits(exp["t"]))
     # ASYNC is refused for host pointers
     assert lib.bspgpu_trace(g.h, segs.ctypes.data, n, res.ctypes.data, 8) < 0
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["rooms8", "city10k", "tilted", "mega200k"])
+def test_start_grid(native, maps, oracle_mod, name):
+    """BSPGPU_OPT_START_GRID: walks that begin below the root are bit-identical to walks from node 0."""
+    from helpers import grid_adversarial_segments
+    from tools import mapgen, seggen
+    m, _ = maps(name)
+    lo, hi = mapgen.seg_bounds(m)
+    segs = np.vstack((_segments(m, 50_000, 30_000, 150_000, 4096), seggen.long_rays(77, 0, 200_000, lo, hi, 0.01, 8.0),
+                      grid_adversarial_segments(m, 300_000)))
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    assert g.info()["start_grid_cells"] > 100_000
+    for variant in ((1, 3) if g.info()["staged_bytes"] < 200 * 1024 else (3, 2)):
+        g.set_option(1, variant)
+        for grid in (1, 0):
+            g.set_option(13, grid)
+            pos = np.zeros((len(segs), 4), np.float32)
+            res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+            _compare(res, pos, exp, exp_pos, f"{name} variant {variant} grid {grid}")
     g.close()

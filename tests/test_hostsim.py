@@ -4,7 +4,7 @@ node/leaf phases the persistent kernel runs -- bit for bit, without a GPU."""
 import numpy as np
 import pytest
 
-from helpers import HostSim, bits, load_golden, mixed_segments
+from helpers import HostSim, bits, grid_adversarial_segments, load_golden, mixed_segments
 
 
 def _check(res, pos, exp, exp_pos, what):
@@ -100,3 +100,24 @@ def test_flatten_rejects_broken_maps(maps):
             arr[key][idx] = val
         with pytest.raises(ValueError, match=what):
             HostSim(bad)
+
+
+@pytest.mark.parametrize("name", ["rooms8", "city10k", "tilted", "mega200k"])
+def test_start_grid_is_bit_identical(oracle_mod, maps, name):
+    """segments whose endpoints share a start-grid cell begin below the root (map_layout.h: StartGridDesc);
+    that must not change a single bit, in particular for endpoints on cell borders and next to node planes."""
+    from tools import mapgen, seggen
+    m, _ = maps(name)
+    sim = HostSim(m)
+    assert 100_000 < sim.layout()["grid_cells"] <= 1_200_000
+    lo, hi = mapgen.seg_bounds(m)
+    segs = np.vstack((mixed_segments(m, 50_000, 30_000, 100_000, 4096), seggen.long_rays(77, 0, 150_000, lo, hi, 0.01, 8.0),
+                      grid_adversarial_segments(m, 200_000)))
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    res, pos = sim.trace(segs, (0, 0), grid=True)
+    _check(res, pos, exp, exp_pos, f"{name} start grid")
+
+
+def test_maps_without_world_bounds_have_no_grid(maps):
+    m, _ = maps("kat1")
+    assert HostSim(m).layout()["grid_cells"] == 0

@@ -661,6 +661,8 @@ def tilted(seed: int = 9, n_brushes: int = 260, leaf_max: int = 1, max_depth: in
     node_arr = np.zeros(len(nodes), ibsp.NODE_DT)
     for i, (pidx, c0, c1) in enumerate(nodes):
         node_arr[i] = (pidx, (c0, c1), (0, 0, 0), (0, 0, 0))
+    node_arr[0]["mins"] = (-W - 150,) * 3            # q3map writes node bounds; the root's are the world box
+    node_arr[0]["maxs"] = (W + 150,) * 3
     leaf_arr = np.zeros(len(leaves), ibsp.LEAF_DT)
     off = 0
     for i, ids in enumerate(leaves):
