@@ -27,7 +27,31 @@ struct Sim {
 std::string g_err;
 }
 
+/* ImageMap that counts record fetches (for sizing the start grid, not used by the parity tests) */
+struct CountingMap {
+	ImageMap m;
+	mutable uint64_t nodes = 0, refs = 0, sides = 0;
+	void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const { nodes++; m.node( i, nx, ny, nz, d, c0, c1 ); }
+	void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const { refs++; m.ref( i, first, nraw, brush ); }
+	void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const { sides++; m.side( i, nx, ny, nz, d ); }
+};
+
 extern "C" {
+
+/* record fetches of the phased walk over n segments, with or without the start grid: out = {nodes, refs, sides, started below the root} */
+void hostsim_count( void * h, const float * segs, uint64_t stride, uint64_t end_off, uint64_t n, int use_grid, uint64_t * out ) {
+	const Sim * s = ( const Sim * ) h;
+	CountingMap cm; cm.m = s->view;
+	uint64_t below = 0;
+	for( uint64_t i = 0; i < n; i++ ) {
+		const float * a = segs + i * stride;
+		const float * b = a + end_off;
+		Ray r; HitState hs;
+		if( use_grid && grid_start_ref( s->grid, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ] ) != 0 ) below++;
+		trace_one_phased< CountingMap, 64 >( cm, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], 8, 8, r, hs, use_grid ? &s->grid : nullptr );
+	}
+	out[ 0 ] = cm.nodes; out[ 1 ] = cm.refs; out[ 2 ] = cm.sides; out[ 3 ] = below;
+}
 
 void * hostsim_create( const bspgpu_map_desc * lumps ) {
 	Sim * s = new Sim();
