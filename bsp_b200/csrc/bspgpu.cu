@@ -72,7 +72,12 @@ template< int M >
 TraceKernel pick_stack( int depth, int threads, int sched ) {
 	return depth <= 32 ? pick_threads< M, 32 >( threads, sched ) : pick_threads< M, 64 >( threads, sched );
 }
+TraceKernel pick_simple( int depth, int threads ) {
+	if( depth <= 32 ) return threads <= 256 ? trace_simple< kGlobal, 32, 256 > : trace_simple< kGlobal, 32, 1024 >;
+	return threads <= 256 ? trace_simple< kGlobal, 64, 256 > : trace_simple< kGlobal, 64, 1024 >;
+}
 TraceKernel pick_kernel( int mode, int depth, int threads, int sched ) {
+	if( sched == 4 ) return pick_simple( depth, threads );
 	switch( mode ) {
 		case kSmemAll: return pick_stack< kSmemAll >( depth, threads, sched );
 		case kSmemTop: return pick_stack< kSmemTop >( depth, threads, sched );
@@ -129,6 +134,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 		/* AUTO (measured on B200, profiles/): the whole map in shared memory when it fits; otherwise the read-only
 		 * global path -- for a few-MB map L1 already keeps the top of the tree resident and staging it buys nothing */
 		if( variant == BSPGPU_VARIANT_AUTO ) variant = h->lay.staged_bytes <= smem_cap ? BSPGPU_VARIANT_SMEM : BSPGPU_VARIANT_GLOBAL;
+		if( h->opt_sched == 4 ) variant = BSPGPU_VARIANT_GLOBAL;   /* the one-thread-per-segment kernel stages nothing */
 		int mode; uint32_t smem = 0, top_nodes = 0;
 		if( variant == BSPGPU_VARIANT_SMEM ) {
 			if( h->lay.staged_bytes > smem_cap ) return fail( BSPGPU_E_INVALID, "SMEM variant: flattened map does not fit in shared memory" );
@@ -164,7 +170,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 		if( occ < 1 ) return fail( BSPGPU_E_CUDA, "kernel does not fit on an SM with the requested block size / shared memory" );
 		if( ctas <= 0 || ctas > occ ) ctas = occ;
 		h->cfg_kernel = kernel; h->cfg_variant = variant; h->cfg_mode = mode; h->cfg_threads = threads;
-		h->cfg_grid = h->sm_count * ctas; h->cfg_smem = smem; h->cfg_staged = staged; h->cfg_top_nodes = top_nodes;
+		h->cfg_grid = h->sm_count * ctas * ( h->opt_sched == 4 ? 4 : 1 ); h->cfg_smem = smem; h->cfg_staged = staged; h->cfg_top_nodes = top_nodes;
 		h->cfg_valid = true;
 	}
 	TraceKernel kernel = h->cfg_kernel;

@@ -490,6 +490,43 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 	if( lane == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
 }
 
+/* ---------------------------------------------------------------- one thread per segment, no scheduling
+ *
+ * BSPGPU_OPT_SCHEDULER=4.  Grid-stride loop, each thread walks its segment start to finish.  No work
+ * fetch, no phases, no compaction: for workloads whose walks are a handful of steps (short moves that
+ * begin at a start-grid reference) the persistent kernel's bookkeeping costs more than divergence does. */
+template< int kMode, int kStack, int kMaxThreads >
+__global__ void __launch_bounds__( kMaxThreads ) trace_simple( const TraceParams p ) {
+	static_assert( kMode == kGlobal, "the simple kernel reads the map through the read-only path" );
+	GlobalMap map;
+	map.nodes = reinterpret_cast< const NodeRec * >( p.image );
+	map.refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
+	map.sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
+	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
+	StackEntry16 stack[ kStack ];
+	uint32_t my_hits = 0;
+	for( uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x; seg < p.n; seg += gridDim.x * blockDim.x ) {
+		Lane l;
+		lane_load_segment( p, seg, l );
+		while( !lane_done( l ) ) {
+			lane_node_phase( map, l, stack, 0xffffffffu );
+			lane_leaf_phase( map, l, stack, 0xffffffffu );
+		}
+		HitState h;
+		lane_hit_state( l, h );
+		const ResultRec o = make_result( h, side_plane );
+		if( p.out ) st_stream4( p.out + seg, o.t, __int_as_float( o.plane ), __int_as_float( o.brush ), __uint_as_float( o.flags ) );
+		if( p.pos ) {
+			float px, py, pz;
+			make_pos( l.r, h, px, py, pz );
+			st_stream4( p.pos + seg, px, py, pz, h.t );
+		}
+		my_hits += ( uint32_t ) h.hit;
+	}
+	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( 0xffffffffu, my_hits, o );
+	if( ( threadIdx.x & 31u ) == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
+}
+
 /* ---------------------------------------------------------------- K1 with two segments per lane
  *
  * Two-phase scheduling of independent lanes tops out near 55 % SIMT utilisation: a lane is in one

@@ -107,7 +107,8 @@ enum {
 	BSPGPU_OPT_MAX_STEPS = 7,       /* node steps a lane takes per round before the warp re-converges */
 	BSPGPU_OPT_BLOCK_SEGS = 8,      /* consecutive segments a warp claims per global atomic (multiple of 32) */
 	BSPGPU_OPT_SCHEDULER = 9,       /* 0 = phase-scheduled lanes (default), 1 = round-based while-while kernel,
-	                                   2 = phase-scheduled at <= 40 registers (1536 threads/SM), 3 = two segments per lane (experimental) */
+	                                   2 = phase-scheduled at <= 40 registers (1536 threads/SM), 3 = two segments per lane (experimental),
+	                                   4 = one thread per segment, no scheduling (GLOBAL only; for very short walks) */
 	BSPGPU_OPT_SIDE_STEPS = 10,     /* brush-side steps a lane takes per leaf phase */
 	BSPGPU_OPT_LEAF_THRESHOLD = 11, /* lanes waiting in a leaf that make a warp run a leaf phase (1..32) */
 	BSPGPU_OPT_MAX_LAUNCH_SEGMENTS = 12, /* segments per kernel launch, default and maximum 2^30 (in-kernel indices are 32-bit) */

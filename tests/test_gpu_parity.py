@@ -276,7 +276,7 @@ def test_both_schedulers_agree(native, maps, oracle_mod, mapname):
     segs = _segments(m, 100_000, 200_000, 50_000, 4096)
     exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
     g = native.BspGpu(m)
-    for sched in (0, 1):
+    for sched in (0, 1, 2, 4):
         g.set_option(9, sched)
         res = g.trace(segs)
         _compare(res, None, exp, exp_pos, f"scheduler {sched}")
