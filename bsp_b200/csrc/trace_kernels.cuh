@@ -201,33 +201,27 @@ template<> struct MapOf< kSmemAll > { typedef SmemAllMap type; };
 template<> struct MapOf< kSmemTop > { typedef SmemTopMap type; };
 template<> struct MapOf< kGlobal > { typedef GlobalMap type; };
 
-/* ---------------------------------------------------------------- K1/K2 */
-
-template< int kMode, int kStack, int kMaxThreads >
-__global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TraceParams p ) {
-	extern __shared__ __align__( 128 ) unsigned char smem[];
-	__shared__ __align__( 8 ) uint64_t stage_bar;
-
-	/* ---- stage the map (or its top) into shared memory: one thread issues TMA bulk copies,
-	 *      everyone waits on the mbarrier's transaction count */
+/* Stage what this mode keeps in shared memory -- one thread issues TMA bulk copies (cp.async.bulk, 32 KB each),
+ * everyone waits on the mbarrier's transaction count -- and bind the map accessor to shared / global memory. */
+template< int kMode >
+__device__ __forceinline__ void stage_and_bind( const TraceParams & p, unsigned char * smem, uint64_t * stage_bar, typename MapOf< kMode >::type & map ) {
 	if( kMode != kGlobal && p.staged_bytes > 0 ) {
 		if( threadIdx.x == 0 ) {
-			mbar_init( &stage_bar, 1 );
+			mbar_init( stage_bar, 1 );
 			mbar_fence_init();
 		}
 		__syncthreads();
 		if( threadIdx.x == 0 ) {
-			mbar_expect_tx( &stage_bar, p.staged_bytes );
+			mbar_expect_tx( stage_bar, p.staged_bytes );
 			const uint32_t kChunk = 32768;
 			for( uint32_t off = 0; off < p.staged_bytes; off += kChunk ) {
 				const uint32_t sz = min( kChunk, p.staged_bytes - off );
-				bulk_g2s( smem + off, p.image + off, sz, &stage_bar );
+				bulk_g2s( smem + off, p.image + off, sz, stage_bar );
 			}
 		}
-		mbar_wait( &stage_bar, 0 );
+		mbar_wait( stage_bar, 0 );
 	}
 
-	typename MapOf< kMode >::type map;
 	const NodeRec * g_nodes = reinterpret_cast< const NodeRec * >( p.image );
 	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
 	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
@@ -244,6 +238,19 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TracePa
 	else {
 		map.nodes = g_nodes; map.refs = g_refs; map.sides = g_sides;
 	}
+}
+
+/* ---------------------------------------------------------------- K1/K2 */
+
+template< int kMode, int kStack, int kMaxThreads >
+__global__ void __launch_bounds__( kMaxThreads ) trace_persistent( const TraceParams p ) {
+	extern __shared__ __align__( 128 ) unsigned char smem[];
+	__shared__ __align__( 8 ) uint64_t stage_bar;
+
+	/* ---- stage the map (or its top) into shared memory: one thread issues TMA bulk copies,
+	 *      everyone waits on the mbarrier's transaction count */
+	typename MapOf< kMode >::type map;
+	stage_and_bind< kMode >( p, smem, &stage_bar, map );
 	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
 
 	const unsigned lane = threadIdx.x & 31u;
@@ -382,40 +389,8 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 	extern __shared__ __align__( 128 ) unsigned char smem[];
 	__shared__ __align__( 8 ) uint64_t stage_bar;
 
-	if( kMode != kGlobal && p.staged_bytes > 0 ) {
-		if( threadIdx.x == 0 ) {
-			mbar_init( &stage_bar, 1 );
-			mbar_fence_init();
-		}
-		__syncthreads();
-		if( threadIdx.x == 0 ) {
-			mbar_expect_tx( &stage_bar, p.staged_bytes );
-			const uint32_t kChunk = 32768;
-			for( uint32_t off = 0; off < p.staged_bytes; off += kChunk ) {
-				const uint32_t sz = min( kChunk, p.staged_bytes - off );
-				bulk_g2s( smem + off, p.image + off, sz, &stage_bar );
-			}
-		}
-		mbar_wait( &stage_bar, 0 );
-	}
-
 	typename MapOf< kMode >::type map;
-	const NodeRec * g_nodes = reinterpret_cast< const NodeRec * >( p.image );
-	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
-	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
-	if constexpr( kMode == kSmemAll ) {
-		map.nodes = opaque_u32( smem_u32( smem ) );
-		map.refs = opaque_u32( map.nodes + ( uint32_t ) p.off_refs );
-		map.sides = opaque_u32( map.nodes + ( uint32_t ) p.off_sides );
-	}
-	else if constexpr( kMode == kSmemTop ) {
-		map.top = opaque_u32( smem_u32( smem ) );
-		map.top_nodes = p.top_nodes;
-		map.g.nodes = g_nodes; map.g.refs = g_refs; map.g.sides = g_sides;
-	}
-	else {
-		map.nodes = g_nodes; map.refs = g_refs; map.sides = g_sides;
-	}
+	stage_and_bind< kMode >( p, smem, &stage_bar, map );
 	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
 
 	const unsigned lane = threadIdx.x & 31u;
@@ -581,40 +556,8 @@ __global__ void __launch_bounds__( kMaxThreads, 1 ) trace_dual( const TraceParam
 	extern __shared__ __align__( 128 ) unsigned char smem[];
 	__shared__ __align__( 8 ) uint64_t stage_bar;
 
-	if( kMode != kGlobal && p.staged_bytes > 0 ) {
-		if( threadIdx.x == 0 ) {
-			mbar_init( &stage_bar, 1 );
-			mbar_fence_init();
-		}
-		__syncthreads();
-		if( threadIdx.x == 0 ) {
-			mbar_expect_tx( &stage_bar, p.staged_bytes );
-			const uint32_t kChunk = 32768;
-			for( uint32_t off = 0; off < p.staged_bytes; off += kChunk ) {
-				const uint32_t sz = min( kChunk, p.staged_bytes - off );
-				bulk_g2s( smem + off, p.image + off, sz, &stage_bar );
-			}
-		}
-		mbar_wait( &stage_bar, 0 );
-	}
-
 	typename MapOf< kMode >::type map;
-	const NodeRec * g_nodes = reinterpret_cast< const NodeRec * >( p.image );
-	const BrushRef * g_refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
-	const SideRec * g_sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
-	if constexpr( kMode == kSmemAll ) {
-		map.nodes = opaque_u32( smem_u32( smem ) );
-		map.refs = opaque_u32( map.nodes + ( uint32_t ) p.off_refs );
-		map.sides = opaque_u32( map.nodes + ( uint32_t ) p.off_sides );
-	}
-	else if constexpr( kMode == kSmemTop ) {
-		map.top = opaque_u32( smem_u32( smem ) );
-		map.top_nodes = p.top_nodes;
-		map.g.nodes = g_nodes; map.g.refs = g_refs; map.g.sides = g_sides;
-	}
-	else {
-		map.nodes = g_nodes; map.refs = g_refs; map.sides = g_sides;
-	}
+	stage_and_bind< kMode >( p, smem, &stage_bar, map );
 	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
 
 	/* parking area right behind the staged bytes (sections are 128-byte aligned) */
