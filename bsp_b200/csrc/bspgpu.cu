@@ -313,7 +313,11 @@ int bspgpu_create_from_file( bspgpu_t ** out, const char * path, int device ) {
 void bspgpu_destroy( bspgpu_t * h ) {
 	if( !h ) return;
 	cudaSetDevice( h->device );
+	/* nothing of this handle may still be in flight when its buffers go away (BSPGPU_ASYNC work on a caller's stream included) */
 	if( h->own_stream ) cudaStreamSynchronize( h->own_stream );
+	if( h->use_user_stream ) cudaStreamSynchronize( h->user_stream );
+	if( h->copy_in ) cudaStreamSynchronize( h->copy_in );
+	if( h->copy_out ) cudaStreamSynchronize( h->copy_out );
 	for( int b = 0; b < kBufs; b++ ) {
 		if( h->d_in[ b ] ) cudaFree( h->d_in[ b ] );
 		if( h->d_out[ b ] ) cudaFree( h->d_out[ b ] );
