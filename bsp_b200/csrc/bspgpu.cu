@@ -210,7 +210,8 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 	return BSPGPU_OK;
 }
 
-int ensure_staging( bspgpu * h, size_t segs, bool want_out, bool want_pos ) {
+/* device staging buffers of the host-pointer pipeline: kBufs chunks of each kind that is actually needed */
+int ensure_staging( bspgpu * h, size_t segs, bool want_in, bool want_out, bool want_pos ) {
 	if( h->buf_segs < segs ) {
 		for( int b = 0; b < kBufs; b++ ) {
 			if( h->d_in[ b ] ) cudaFree( h->d_in[ b ] );
@@ -218,11 +219,10 @@ int ensure_staging( bspgpu * h, size_t segs, bool want_out, bool want_pos ) {
 			if( h->d_pos[ b ] ) cudaFree( h->d_pos[ b ] );
 			h->d_in[ b ] = h->d_out[ b ] = h->d_pos[ b ] = nullptr;
 		}
-		h->buf_segs = 0;
-		for( int b = 0; b < kBufs; b++ ) CK( cudaMalloc( &h->d_in[ b ], segs * sizeof( bspgpu_segment ) ) );
 		h->buf_segs = segs;
 	}
 	for( int b = 0; b < kBufs; b++ ) {
+		if( want_in && !h->d_in[ b ] ) CK( cudaMalloc( &h->d_in[ b ], h->buf_segs * sizeof( bspgpu_segment ) ) );
 		if( want_out && !h->d_out[ b ] ) CK( cudaMalloc( &h->d_out[ b ], h->buf_segs * sizeof( bspgpu_result ) ) );
 		if( want_pos && !h->d_pos[ b ] ) CK( cudaMalloc( &h->d_pos[ b ], h->buf_segs * sizeof( bspgpu_pos ) ) );
 	}
@@ -369,7 +369,7 @@ int bspgpu_trace_pos( bspgpu_t * h, const void * segs, uint64_t n, bspgpu_result
 	if( chunk > n ) chunk = n;
 	if( chunk > kMaxLaunchSegs ) chunk = kMaxLaunchSegs;
 	{
-		const int rc = ensure_staging( h, ( size_t ) chunk, out != nullptr, pos != nullptr );
+		const int rc = ensure_staging( h, ( size_t ) chunk, !segs_dev, out && !out_dev, pos && !out_dev );
 		if( rc != BSPGPU_OK ) return rc;
 	}
 	/* order the side streams after whatever the compute stream already holds */
