@@ -24,6 +24,7 @@ using namespace bspk;
 
 static_assert( sizeof( bspgpu_result ) == sizeof( ResultRec ) && sizeof( ResultRec ) == 16, "result wire format" );
 static_assert( sizeof( bspgpu_segment ) == 32 && sizeof( bspgpu_pos ) == 16, "segment wire format" );
+static_assert( sizeof( QNodeRec ) == 32, "image records" );
 static_assert( sizeof( NodeRec ) == 32 && sizeof( BrushRef ) == 16 && sizeof( SideRec ) == 16, "image records" );
 
 namespace {
@@ -49,6 +50,7 @@ typedef void ( *TraceKernel )( const TraceParams );
 
 template< int M, int S >
 TraceKernel pick_threads( int threads, int sched ) {
+	if constexpr( M != kGlobalPacked ) {   /* the experimental schedulers walk NodeRecs only */
 	if( sched == 1 ) {
 		if( threads <= 256 ) return trace_persistent< M, S, 256 >;
 		if( threads <= 512 ) return trace_persistent< M, S, 512 >;
@@ -59,12 +61,13 @@ TraceKernel pick_threads( int threads, int sched ) {
 		if( threads <= 512 ) return trace_dual< M, S, 512 >;
 		return trace_dual< M, S, 1024 >;
 	}
+	}
 	if( sched == 2 ) {   /* experiment: 1536 threads per SM (<= 40 registers) */
 		if( threads <= 256 ) return trace_phased< M, S, 256, 6 >;
 		if( threads <= 512 ) return trace_phased< M, S, 512, 3 >;
 		return trace_phased< M, S, 768, 2 >;
 	}
-	if( threads <= 256 ) return trace_phased< M, S, 256, 1 >;
+	if( threads <= 256 ) return trace_phased< M, S, 256, M == kGlobalPacked ? 5 : 1 >;   /* 5 CTAs of 256 threads per SM: <= 51 registers */
 	if( threads <= 512 ) return trace_phased< M, S, 512, 1 >;
 	return trace_phased< M, S, 1024, 1 >;
 }
@@ -81,6 +84,7 @@ TraceKernel pick_kernel( int mode, int depth, int threads, int sched ) {
 	switch( mode ) {
 		case kSmemAll: return pick_stack< kSmemAll >( depth, threads, sched );
 		case kSmemTop: return pick_stack< kSmemTop >( depth, threads, sched );
+		case kGlobalPacked: return pick_stack< kGlobalPacked >( depth, threads, sched );
 		default: return pick_stack< kGlobal >( depth, threads, sched );
 	}
 }
@@ -102,6 +106,7 @@ struct bspgpu {
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 96 * 1024;
 	int64_t opt_chunk = 2ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;   /* 0 = per-variant default */
 	int64_t opt_sched = 0, opt_side_steps = 8, opt_leaf_threshold = 16;
+	int64_t opt_packed_nodes = 0;  /* 1: two-level node records on the read-only path (measured slower, profiles/README.md; kept as a tested option) */
 	int64_t opt_start_grid = -1;   /* -1 auto: on unless the whole map sits in shared memory (there a node step is cheaper than the grid's global load) */
 	uint64_t opt_max_launch = kMaxLaunchSegs;   /* segments per kernel launch (lowered by tests to exercise the multi-launch path) */
 
@@ -149,7 +154,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 			top_nodes = ( uint32_t ) ( bytes / sizeof( NodeRec ) );
 			smem = top_nodes * ( uint32_t ) sizeof( NodeRec );
 		}
-		else mode = kGlobal;
+		else mode = ( h->opt_packed_nodes > 0 && ( h->opt_sched == 0 || h->opt_sched == 2 ) ) ? kGlobalPacked : kGlobal;
 
 		int threads = ( int ) h->opt_threads;
 		if( threads <= 0 ) threads = ( mode == kSmemAll ) ? 1024 : 256;   /* measured: 1 x 1024 with the map in smem, 5 x 256 otherwise */
@@ -179,7 +184,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 
 	TraceParams p;
 	p.image = h->d_image;
-	p.off_refs = h->lay.off_refs; p.off_sides = h->lay.off_sides; p.off_side_plane = h->lay.off_side_plane;
+	p.off_refs = h->lay.off_refs; p.off_sides = h->lay.off_sides; p.off_side_plane = h->lay.off_side_plane; p.off_qnodes = h->lay.off_qnodes;
 	p.staged_bytes = h->cfg_staged; p.top_nodes = top_nodes;
 	p.block_segs = ( uint32_t ) ( ( h->opt_block_segs + 31 ) / 32 * 32 );
 	p.refill = ( uint32_t ) ( h->opt_refill < 1 ? 1 : ( h->opt_refill > 32 ? 32 : h->opt_refill ) );
@@ -511,6 +516,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 		case BSPGPU_OPT_SCHEDULER: h->opt_sched = value; break;
 		case BSPGPU_OPT_SIDE_STEPS: h->opt_side_steps = value; break;
 		case BSPGPU_OPT_LEAF_THRESHOLD: h->opt_leaf_threshold = value; break;
+		case BSPGPU_OPT_PACKED_NODES: h->opt_packed_nodes = value > 0 ? 1 : 0; break;
 		case BSPGPU_OPT_START_GRID: h->opt_start_grid = value < 0 ? -1 : ( value ? 1 : 0 ); break;
 		case BSPGPU_OPT_MAX_LAUNCH_SEGMENTS:
 			if( value < 32 || ( uint64_t ) value > kMaxLaunchSegs ) return fail( BSPGPU_E_INVALID, "max launch segments must be in [32, 2^30]" );

@@ -154,7 +154,54 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	lay.off_sides = align_up( lay.off_refs + ( uint64_t ) orefs.size() * sizeof( BrushRef ), kSectionAlign );
 	lay.staged_bytes = align_up( lay.off_sides + ( uint64_t ) num_sides_out * sizeof( SideRec ), kSectionAlign );
 	lay.off_side_plane = lay.staged_bytes;
-	lay.off_grid = align_up( lay.off_side_plane + ( uint64_t ) num_sides_out * sizeof( uint32_t ), kSectionAlign );
+	lay.off_qnodes = align_up( lay.off_side_plane + ( uint64_t ) num_sides_out * sizeof( uint32_t ), kSectionAlign );
+	lay.off_grid = align_up( lay.off_qnodes + ( uint64_t ) num_nodes * sizeof( QNodeRec ), kSectionAlign );
+
+	/* ---- two-level records for the read-only-path walk (map_layout.h: QNodeRec) */
+	std::vector< QNodeRec > qnodes( num_nodes );
+	{
+		auto axis_of = [&]( const NodeRec & n ) -> int {   /* 0/1/2 for a bitwise +unit normal, else -1 */
+			uint32_t b[ 3 ];
+			memcpy( b, &n.nx, 12 );
+			const uint32_t one = 0x3f800000u;
+			if( b[ 0 ] == one && b[ 1 ] == 0 && b[ 2 ] == 0 ) return 0;
+			if( b[ 0 ] == 0 && b[ 1 ] == one && b[ 2 ] == 0 ) return 1;
+			if( b[ 0 ] == 0 && b[ 1 ] == 0 && b[ 2 ] == one ) return 2;
+			return -1;
+		};
+		auto bits = []( float f ) { uint32_t u; memcpy( &u, &f, 4 ); return u; };
+		const bool disable = getenv( "BSPGPU_NO_PACKED_NODES" ) != nullptr;   /* test knob: general records only */
+		for( uint32_t i = 0; i < num_nodes; i++ ) {
+			const NodeRec & n = onodes[ i ];
+			QNodeRec & q = qnodes[ i ];
+			const int ax = disable ? -1 : axis_of( n );
+			if( ax < 0 ) {
+				q.w[ 0 ] = bits( n.nx ); q.w[ 1 ] = bits( n.ny ); q.w[ 2 ] = bits( n.nz ); q.w[ 3 ] = bits( n.d );
+				q.w[ 4 ] = ( uint32_t ) n.child[ 0 ]; q.w[ 5 ] = ( uint32_t ) n.child[ 1 ]; q.w[ 6 ] = 0; q.w[ 7 ] = 0;
+				continue;
+			}
+			uint32_t w = kQPacked | ( ( uint32_t ) ax << kQAxisShift );
+			uint32_t base = 0;
+			bool have_base = false;
+			q.w[ 0 ] = bits( n.d ); q.w[ 1 ] = 0; q.w[ 2 ] = 0;
+			for( int k = 0; k < 2; k++ ) {
+				const int32_t c = n.child[ k ];
+				uint32_t g_a = ( uint32_t ) c, g_b = 0;          /* not expanded: the child's own reference */
+				const int cax = c >= 0 ? axis_of( onodes[ c ] ) : -1;
+				const bool fits = c >= 0 && ( uint32_t ) c < ( 1u << ( 32 - kQBaseShift ) );
+				const bool consecutive = !have_base || ( uint32_t ) c == base + 1;   /* breadth-first numbering; checked, not assumed */
+				if( cax >= 0 && fits && consecutive ) {
+					w |= k == 0 ? kQExpand0 : kQExpand1;
+					w |= ( uint32_t ) cax << ( k == 0 ? kQAxis0Shift : kQAxis1Shift );
+					q.w[ 1 + k ] = bits( onodes[ c ].d );
+					g_a = ( uint32_t ) onodes[ c ].child[ 0 ]; g_b = ( uint32_t ) onodes[ c ].child[ 1 ];
+					if( !have_base ) { base = ( uint32_t ) c; have_base = true; }
+				}
+				q.w[ 3 + 2 * k ] = g_a; q.w[ 4 + 2 * k ] = g_b;
+			}
+			q.w[ 7 ] = w | ( base << kQBaseShift );
+		}
+	}
 
 	/* ---- start grid (map_layout.h).  World box = the root node's bounds (reference bsp.h:63-64 mins/maxs, unused
 	 *      by the reference's trace); no grid when a map does not carry them. */
@@ -237,6 +284,7 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	out.image.assign( lay.total_bytes, 0 );
 	memcpy( out.image.data() + lay.off_nodes, onodes.data(), onodes.size() * sizeof( NodeRec ) );
 	if( !orefs.empty() ) memcpy( out.image.data() + lay.off_refs, orefs.data(), orefs.size() * sizeof( BrushRef ) );
+	memcpy( out.image.data() + lay.off_qnodes, qnodes.data(), qnodes.size() * sizeof( QNodeRec ) );
 	SideRec * osides = ( SideRec * ) ( out.image.data() + lay.off_sides );
 	uint32_t * oside_plane = ( uint32_t * ) ( out.image.data() + lay.off_side_plane );
 	for( uint32_t s = 0; s < L.num_brush_sides; s++ ) {

@@ -24,6 +24,8 @@
 #ifndef BSPGPU_TRACE_CORE_H
 #define BSPGPU_TRACE_CORE_H
 
+#include <string.h>
+
 #include "map_layout.h"
 
 #ifdef __CUDACC__
@@ -294,10 +296,8 @@ BSPK_HD void lane_hit_state( const Lane & l, HitState & h ) {
  *   near child has work            -> go there over [tmin, u or tmax]; push the far child over [u, tmax] if it has work
  *   near child is an empty leaf    -> go straight to the far child over [u, tmax] if the segment straddles and it has work
  *   neither                        -> next pending far side from the stack (the second recursive call, :250-252), or done */
-template< class Map >
-BSPK_HD void lane_node_step( const Map & map, Lane & l, StackEntry16 * stack ) {
-	float nx, ny, nz, d; int32_t c0, c1;
-	map.node( l.cur, nx, ny, nz, d, c0, c1 );
+/* returns the child slot the walk continued into (0 front, 1 back), or 2 when it continued from the stack / finished */
+BSPK_HD int32_t lane_node_apply( Lane & l, StackEntry16 * stack, float nx, float ny, float nz, float d, int32_t c0, int32_t c1 ) {
 	const float denom = dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );                /* :220 */
 	const float dist = -( dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d );        /* :221 */
 	const float u = dist / denom;                                                  /* :227 */
@@ -323,12 +323,56 @@ BSPK_HD void lane_node_step( const Map & map, Lane & l, StackEntry16 * stack ) {
 	l.tmax = near_ok ? ( both ? u : l.tmax ) : top.tmax;                           /* top.tmax == l.tmax unless popped */
 	l.sp += ( do_push ? 1 : 0 ) - ( can_pop ? 1 : 0 );
 	l.s = 0; l.s_end = 0;                                                          /* if this was a leaf: fetch its first brush reference */
+	return do_pop ? 2 : ( ( near_back == near_ok ) ? 1 : 0 );                      /* near taken: slot near_back; far taken: the other one */
+}
+
+template< class Map >
+BSPK_HD void lane_node_step( const Map & map, Lane & l, StackEntry16 * stack ) {
+	float nx, ny, nz, d; int32_t c0, c1;
+	map.node( l.cur, nx, ny, nz, d, c0, c1 );
+	lane_node_apply( l, stack, nx, ny, nz, d, c0, c1 );
+}
+
+BSPK_HD float bits_to_float( uint32_t u ) {
+#ifdef __CUDA_ARCH__
+	return __uint_as_float( u );
+#else
+	float f; memcpy( &f, &u, 4 ); return f;
+#endif
+}
+
+/* the same step on a QNodeRec (map_layout.h): one record fetch, one or two tree levels.  A packed record's plane is
+ * rebuilt as the exact unit normal it stands for and goes through lane_node_apply like any other plane, so the
+ * arithmetic -- and the result -- is that of two lane_node_steps; only the second record fetch is gone. */
+template< class Map >
+BSPK_HD void lane_qnode_step( const Map & map, Lane & l, StackEntry16 * stack ) {
+	uint32_t q0, q1, q2, q3, q4, q5, q6, w;
+	map.qnode( l.cur, q0, q1, q2, q3, q4, q5, q6, w );
+	if( !( w & kQPacked ) ) {
+		lane_node_apply( l, stack, bits_to_float( q0 ), bits_to_float( q1 ), bits_to_float( q2 ), bits_to_float( q3 ), ( int32_t ) q4, ( int32_t ) q5 );
+		return;
+	}
+	const uint32_t base = w >> kQBaseShift;
+	const bool e0 = ( w & kQExpand0 ) != 0, e1 = ( w & kQExpand1 ) != 0;
+	const uint32_t ax = ( w >> kQAxisShift ) & 3u;
+	const int32_t c0 = e0 ? ( int32_t ) base : ( int32_t ) q3;
+	const int32_t c1 = e1 ? ( int32_t ) ( base + ( e0 ? 1u : 0u ) ) : ( int32_t ) q5;
+	const int32_t took = lane_node_apply( l, stack, ax == 0u ? 1.0f : 0.0f, ax == 1u ? 1.0f : 0.0f, ax == 2u ? 1.0f : 0.0f, bits_to_float( q0 ), c0, c1 );
+	const bool second = took == 0 ? e0 : ( took == 1 ? e1 : false );
+	if( second ) {
+		const uint32_t ax2 = ( w >> ( took ? kQAxis1Shift : kQAxis0Shift ) ) & 3u;
+		lane_node_apply( l, stack, ax2 == 0u ? 1.0f : 0.0f, ax2 == 1u ? 1.0f : 0.0f, ax2 == 2u ? 1.0f : 0.0f,
+		                 bits_to_float( took ? q2 : q1 ), ( int32_t ) ( took ? q5 : q3 ), ( int32_t ) ( took ? q6 : q4 ) );
+	}
 }
 
 /* up to `max_steps` node steps; stops early when the lane leaves node mode */
 template< class Map >
 BSPK_HD void lane_node_phase( const Map & map, Lane & l, StackEntry16 * stack, uint32_t max_steps ) {
-	while( lane_in_node( l ) && max_steps-- ) lane_node_step( map, l, stack );
+	while( lane_in_node( l ) && max_steps-- ) {
+		if constexpr( Map::kPackedNodes ) lane_qnode_step( map, l, stack );
+		else lane_node_step( map, l, stack );
+	}
 }
 
 /* up to `max_steps` iterations of trace_seg_brush's side loop (bsp.cc:128-165), moving through the
@@ -451,6 +495,7 @@ BSPK_HD void make_pos( const Ray & r, const HitState & h, float & px, float & py
 
 /* plain-pointer accessor over the flattened image (global memory on the device, host memory in hostsim) */
 struct ImageMap {
+	static const bool kPackedNodes = false;
 	const NodeRec * nodes;
 	const BrushRef * refs;
 	const SideRec * sides;
@@ -469,6 +514,16 @@ struct ImageMap {
 	BSPK_HD void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const {
 		const SideRec & s = sides[ i ];
 		nx = s.nx; ny = s.ny; nz = s.nz; d = s.d;
+	}
+};
+
+/* same, walking the two-level QNodeRec section (map_layout.h) */
+struct ImageMapPacked : ImageMap {
+	static const bool kPackedNodes = true;
+	const QNodeRec * qnodes;
+	BSPK_HD void qnode( int32_t i, uint32_t & q0, uint32_t & q1, uint32_t & q2, uint32_t & q3, uint32_t & q4, uint32_t & q5, uint32_t & q6, uint32_t & w ) const {
+		const QNodeRec & q = qnodes[ i ];
+		q0 = q.w[ 0 ]; q1 = q.w[ 1 ]; q2 = q.w[ 2 ]; q3 = q.w[ 3 ]; q4 = q.w[ 4 ]; q5 = q.w[ 5 ]; q6 = q.w[ 6 ]; w = q.w[ 7 ];
 	}
 };
 

@@ -104,11 +104,12 @@ class HostSim:
             raise ValueError(self.l.hostsim_error().decode())
 
     def layout(self):
-        out = np.zeros(7, np.uint64)
+        out = np.zeros(9, np.uint64)
         self.l.hostsim_layout(self.h, out.ctypes.data)
-        return dict(zip(("nodes", "refs", "sides", "depth", "staged_bytes", "total_bytes", "grid_cells"), (int(v) for v in out)))
+        return dict(zip(("nodes", "refs", "sides", "depth", "staged_bytes", "total_bytes", "grid_cells", "packed_nodes", "expanded_children"),
+                        (int(v) for v in out)))
 
-    def trace(self, segs, budgets=None, grid=False):
+    def trace(self, segs, budgets=None, grid=False, packed=False):
         from bsp_b200.api import RESULT_DT
         segs = np.ascontiguousarray(segs, np.float32)
         res = np.zeros(len(segs), RESULT_DT)
@@ -116,7 +117,7 @@ class HostSim:
         if budgets is None:
             self.l.hostsim_trace(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data)
         else:
-            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], 1 if grid else 0)
+            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], (1 if grid else 0) | (2 if packed else 0))
         return res, pos
 
     def leaf(self, pts):

@@ -449,3 +449,25 @@ def test_start_grid(native, maps, oracle_mod, name):
             res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
             _compare(res, pos, exp, exp_pos, f"{name} variant {variant} grid {grid}")
     g.close()
+
+
+@pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k", "tilted", "mega200k"])
+def test_packed_nodes(native, maps, oracle_mod, name):
+    """BSPGPU_OPT_PACKED_NODES: the GLOBAL variant's two-level node records give the same bits as one record per node,
+    with and without the start grid and under small phase budgets (a two-level step may suspend between records only)."""
+    from helpers import grid_adversarial_segments
+    from tools import mapgen, seggen
+    m, _ = maps(name)
+    lo, hi = mapgen.seg_bounds(m)
+    segs = np.vstack((_segments(m, 50_000, 30_000, 150_000, 4096), seggen.long_rays(79, 0, 200_000, lo, hi, 0.01, 8.0)))
+    g = native.BspGpu(m)
+    if g.info()["start_grid_cells"]:
+        segs = np.vstack((segs, grid_adversarial_segments(m, 200_000)))
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g.set_option(1, 3)
+    for packed, grid, steps in ((1, 1, 8), (1, 0, 1), (0, 1, 8), (1, -1, 3)):
+        g.set_option(14, packed); g.set_option(13, grid); g.set_option(7, steps)
+        pos = np.zeros((len(segs), 4), np.float32)
+        res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+        _compare(res, pos, exp, exp_pos, f"{name} packed {packed} grid {grid} steps {steps}")
+    g.close()

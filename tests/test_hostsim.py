@@ -118,6 +118,50 @@ def test_start_grid_is_bit_identical(oracle_mod, maps, name):
     _check(res, pos, exp, exp_pos, f"{name} start grid")
 
 
+@pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "city10k", "tilted", "mega200k"])
+def test_packed_nodes_are_bit_identical(oracle_mod, maps, name):
+    """the read-only-path walk fetches two-level records (map_layout.h: QNodeRec) where node planes are axial:
+    same results bit for bit, with and without the start grid, on fully axial (kd) trees, on the tilted map where
+    packed and general records alternate along a walk, and on the hand-written KAT maps."""
+    from tools import mapgen, seggen
+    m, _ = maps(name)
+    sim = HostSim(m)
+    lay = sim.layout()
+    if name in ("rooms8", "city10k", "mega200k"):
+        assert lay["packed_nodes"] == lay["nodes"] and lay["expanded_children"] == lay["nodes"] - 1
+    if name == "tilted":
+        assert 0 < lay["packed_nodes"] < lay["nodes"] and 0 < lay["expanded_children"] < lay["packed_nodes"]
+    lo, hi = mapgen.seg_bounds(m)
+    segs = np.vstack((mixed_segments(m, 50_000, 30_000, 100_000, 4096), seggen.long_rays(78, 0, 150_000, lo, hi, 0.01, 8.0)))
+    if lay["grid_cells"]:
+        segs = np.vstack((segs, grid_adversarial_segments(m, 100_000)))
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    for grid in (False, True):
+        res, pos = sim.trace(segs, (0, 0), grid=grid, packed=True)
+        _check(res, pos, exp, exp_pos, f"{name} packed nodes, grid {grid}")
+
+
+def test_packed_nodes_only_for_exact_positive_unit_normals(maps):
+    """-1 / -0 / almost-unit normals must stay general records (the kernel rebuilds +unit normals only)"""
+    import copy
+    m, _ = maps("rooms8")
+    full = HostSim(m).layout()
+    for val in (np.float32(-1.0), np.float32(1.0) - np.float32(2.0 ** -24)):
+        bad = copy.deepcopy(m)
+        root_plane = int(bad.nodes["plane"][0])
+        n = bad.planes["n"][root_plane].copy()
+        n[np.argmax(np.abs(n))] = val
+        bad.planes["n"][root_plane] = n
+        lay = HostSim(bad).layout()
+        assert lay["packed_nodes"] < full["packed_nodes"]
+    bad = copy.deepcopy(m)
+    root_plane = int(bad.nodes["plane"][0])
+    n = bad.planes["n"][root_plane].copy()
+    n[np.argmin(np.abs(n))] = np.float32(-0.0)
+    bad.planes["n"][root_plane] = n
+    assert HostSim(bad).layout()["packed_nodes"] < full["packed_nodes"]
+
+
 def test_maps_without_world_bounds_have_no_grid(maps):
     m, _ = maps("kat1")
     assert HostSim(m).layout()["grid_cells"] == 0
