@@ -315,14 +315,18 @@ BSPK_HD int32_t lane_node_apply( Lane & l, StackEntry16 * stack, float nx, float
 	if( do_push ) {
 		StackEntry16 e; e.node = cf; e.tmin = u; e.tmax = l.tmax; e.pad = 0;
 		stack[ l.sp ] = e;
+		l.sp++;
 	}
-	StackEntry16 top; top.node = kCurDone; top.tmin = l.tmin; top.tmax = l.tmax; top.pad = 0;
-	if( can_pop ) top = stack[ l.sp - 1 ];
-	l.cur = near_ok ? cn : ( far_work ? cf : top.node );
-	l.tmin = near_ok ? l.tmin : ( far_work ? u : top.tmin );
-	l.tmax = near_ok ? ( both ? u : l.tmax ) : top.tmax;                           /* top.tmax == l.tmax unless popped */
-	l.sp += ( do_push ? 1 : 0 ) - ( can_pop ? 1 : 0 );
-	l.s = 0; l.s_end = 0;                                                          /* if this was a leaf: fetch its first brush reference */
+	/* continue into the near child, else the far child; with neither, the next pending far side (or done) */
+	l.cur = near_ok ? cn : cf;
+	l.tmax = ( near_ok && both ) ? u : l.tmax;
+	l.tmin = near_ok ? l.tmin : u;
+	if( do_pop ) l.cur = kCurDone;
+	if( can_pop ) {
+		l.sp--;
+		const StackEntry16 top = stack[ l.sp ];
+		l.cur = top.node; l.tmin = top.tmin; l.tmax = top.tmax;
+	}
 	return do_pop ? 2 : ( ( near_back == near_ok ) ? 1 : 0 );                      /* near taken: slot near_back; far taken: the other one */
 }
 
@@ -369,10 +373,12 @@ BSPK_HD void lane_qnode_step( const Map & map, Lane & l, StackEntry16 * stack ) 
 /* up to `max_steps` node steps; stops early when the lane leaves node mode */
 template< class Map >
 BSPK_HD void lane_node_phase( const Map & map, Lane & l, StackEntry16 * stack, uint32_t max_steps ) {
-	while( lane_in_node( l ) && max_steps-- ) {
+	if( !lane_in_node( l ) ) return;
+	for( ; max_steps > 0 && lane_in_node( l ); max_steps-- ) {
 		if constexpr( Map::kPackedNodes ) lane_qnode_step( map, l, stack );
 		else lane_node_step( map, l, stack );
 	}
+	l.s = 0; l.s_end = 0;                                                          /* if the walk reached a leaf: fetch its first brush reference */
 }
 
 /* up to `max_steps` iterations of trace_seg_brush's side loop (bsp.cc:128-165), moving through the
@@ -381,7 +387,7 @@ template< class Map >
 BSPK_HD void lane_leaf_phase( const Map & map, Lane & l, const StackEntry16 * stack, uint32_t max_steps ) {
 	/* end = start + dir * tmax (bsp.cc:121); tmax is the leaf interval's and is constant inside a leaf */
 	float ex = l.r.sx + l.r.dx * l.tmax, ey = l.r.sy + l.r.dy * l.tmax, ez = l.r.sz + l.r.dz * l.tmax;
-	while( lane_in_leaf( l ) && max_steps-- ) {
+	for( ; max_steps > 0 && lane_in_leaf( l ); max_steps-- ) {
 		if( l.s == l.s_end ) {
 			/* next brush of the leaf: reference ~cur; reset the clip state (bsp.cc:122-125) */
 			uint32_t first, nraw;
