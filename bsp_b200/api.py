@@ -15,7 +15,7 @@ HIT, STARTSOLID = 1, 2
 SEGS_DEVICE, OUT_DEVICE, SEGS_PACKED24, ASYNC = 1, 2, 4, 8
 VARIANT_AUTO, VARIANT_SMEM, VARIANT_TOPTREE, VARIANT_GLOBAL = 0, 1, 2, 3
 OPT_VARIANT, OPT_BLOCK_THREADS, OPT_CTAS_PER_SM, OPT_TOPTREE_BYTES, OPT_CHUNK_SEGMENTS, OPT_REFILL, \
-    OPT_MAX_STEPS, OPT_BLOCK_SEGS, OPT_SCHEDULER, OPT_SIDE_STEPS, OPT_LEAF_THRESHOLD, OPT_MAX_LAUNCH_SEGMENTS, OPT_START_GRID, OPT_PACKED_NODES = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
+    OPT_MAX_STEPS, OPT_BLOCK_SEGS, OPT_SCHEDULER, OPT_SIDE_STEPS, OPT_LEAF_THRESHOLD, OPT_MAX_LAUNCH_SEGMENTS, OPT_START_GRID, OPT_PACKED_NODES, OPT_SMEM_STACK = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
 
 # every symbol include/bspgpu.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = (

@@ -79,8 +79,19 @@ TraceKernel pick_simple( int depth, int threads ) {
 	if( depth <= 32 ) return threads <= 256 ? trace_simple< kGlobal, 32, 256 > : trace_simple< kGlobal, 32, 1024 >;
 	return threads <= 256 ? trace_simple< kGlobal, 64, 256 > : trace_simple< kGlobal, 64, 1024 >;
 }
-TraceKernel pick_kernel( int mode, int depth, int threads, int sched ) {
+/* phase-scheduled kernel, read-only map path, 256-thread CTAs, first `slots` stack entries in shared memory */
+template< int S >
+TraceKernel pick_smem_stack( int slots ) {
+	switch( slots ) {
+		case 2: return trace_phased< kGlobal, S, 256, 5, 2 >;
+		case 4: return trace_phased< kGlobal, S, 256, 5, 4 >;
+		case 6: return trace_phased< kGlobal, S, 256, 5, 6 >;
+		default: return trace_phased< kGlobal, S, 256, 5, 8 >;
+	}
+}
+TraceKernel pick_kernel( int mode, int depth, int threads, int sched, int smem_stack ) {
 	if( sched == 4 ) return pick_simple( depth, threads );
+	if( smem_stack > 0 ) return depth <= 32 ? pick_smem_stack< 32 >( smem_stack ) : pick_smem_stack< 64 >( smem_stack );
 	switch( mode ) {
 		case kSmemAll: return pick_stack< kSmemAll >( depth, threads, sched );
 		case kSmemTop: return pick_stack< kSmemTop >( depth, threads, sched );
@@ -105,7 +116,8 @@ struct bspgpu {
 	/* options */
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 96 * 1024;
 	int64_t opt_chunk = 2ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;   /* 0 = per-variant default */
-	int64_t opt_sched = 0, opt_side_steps = 8, opt_leaf_threshold = 16;
+	int64_t opt_sched = 0, opt_side_steps = 6, opt_leaf_threshold = 16;
+	int64_t opt_smem_stack = -1;   /* GLOBAL variant, 256-thread CTAs: traversal-stack slots per thread kept in shared memory (0, 2, 4, 6, 8; -1 auto = 6) */
 	int64_t opt_packed_nodes = 0;  /* 1: two-level node records on the read-only path (measured slower, profiles/README.md; kept as a tested option) */
 	int64_t opt_start_grid = -1;   /* -1 auto: on unless the whole map sits in shared memory (there a node step is cheaper than the grid's global load) */
 	uint64_t opt_max_launch = kMaxLaunchSegs;   /* segments per kernel launch (lowered by tests to exercise the multi-launch path) */
@@ -167,7 +179,13 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 			smem += 96u * ( uint32_t ) threads;   /* parking slots of trace_dual */
 			if( smem > ( uint32_t ) h->max_smem_optin ) return fail( BSPGPU_E_INVALID, "two-segment scheduler: staged map + 96 B/thread of parking slots exceed shared memory" );
 		}
-		TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched );
+		int smem_stack = 0;
+		const int64_t want_stack = h->opt_smem_stack < 0 ? 6 : h->opt_smem_stack;   /* measured: 4 -> +10 %, 6 -> +17 %, 8 -> +10 % on city10k long rays */
+		if( mode == kGlobal && h->opt_sched == 0 && threads <= 256 && want_stack > 0 ) {
+			smem_stack = want_stack <= 2 ? 2 : ( want_stack <= 4 ? 4 : ( want_stack <= 6 ? 6 : 8 ) );
+			smem += ( uint32_t ) smem_stack * 256u * 16u;
+		}
+		TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched, smem_stack );
 		CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );
 		int ctas = ( int ) h->opt_ctas;
 		int occ = 0;
@@ -516,6 +534,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 		case BSPGPU_OPT_SCHEDULER: h->opt_sched = value; break;
 		case BSPGPU_OPT_SIDE_STEPS: h->opt_side_steps = value; break;
 		case BSPGPU_OPT_LEAF_THRESHOLD: h->opt_leaf_threshold = value; break;
+		case BSPGPU_OPT_SMEM_STACK: h->opt_smem_stack = value < 0 ? -1 : value; break;
 		case BSPGPU_OPT_PACKED_NODES: h->opt_packed_nodes = value > 0 ? 1 : 0; break;
 		case BSPGPU_OPT_START_GRID: h->opt_start_grid = value < 0 ? -1 : ( value ? 1 : 0 ); break;
 		case BSPGPU_OPT_MAX_LAUNCH_SEGMENTS:

@@ -248,6 +248,34 @@ BSPK_HD bool lane_in_leaf( const Lane & l ) { return ( uint32_t ) l.cur > ( uint
 BSPK_HD bool lane_done( const Lane & l ) { return l.cur == kCurDone; }
 BSPK_HD bool lane_idle( const Lane & l ) { return l.cur == kCurIdle; }
 
+/* Where the pending far sides live is the caller's business: the step functions below are written against
+ * stack_put / stack_get.  A plain array (local memory on the device) is the default; the kernels add a variant
+ * that keeps the first slots in shared memory (trace_kernels.cuh: SmemStack). */
+BSPK_HD void stack_put( StackEntry16 * s, int32_t i, int32_t node, float tmin, float tmax ) {
+	StackEntry16 e; e.node = node; e.tmin = tmin; e.tmax = tmax; e.pad = 0;
+	s[ i ] = e;
+}
+BSPK_HD void stack_get( const StackEntry16 * s, int32_t i, int32_t & node, float & tmin, float & tmax ) {
+	const StackEntry16 e = s[ i ];
+	node = e.node; tmin = e.tmin; tmax = e.tmax;
+}
+
+/* slots [0, D) in one array, the rest in another -- the host-side model of SmemStack (tests/hostsim) */
+template< int D >
+struct SplitStack {
+	StackEntry16 * lo, * hi;
+};
+template< int D >
+BSPK_HD void stack_put( const SplitStack< D > & s, int32_t i, int32_t node, float tmin, float tmax ) {
+	if( i < D ) stack_put( s.lo, i, node, tmin, tmax );
+	else stack_put( s.hi, i - D, node, tmin, tmax );
+}
+template< int D >
+BSPK_HD void stack_get( const SplitStack< D > & s, int32_t i, int32_t & node, float & tmin, float & tmax ) {
+	if( i < D ) stack_get( s.lo, i, node, tmin, tmax );
+	else stack_get( s.hi, i - D, node, tmin, tmax );
+}
+
 BSPK_HD void lane_start( Lane & l, float sx, float sy, float sz, float ex, float ey, float ez ) {
 	l.r.sx = sx; l.r.sy = sy; l.r.sz = sz;
 	l.r.dx = ex - sx; l.r.dy = ey - sy; l.r.dz = ez - sz;      /* bsp.cc:261 */
@@ -297,7 +325,8 @@ BSPK_HD void lane_hit_state( const Lane & l, HitState & h ) {
  *   near child is an empty leaf    -> go straight to the far child over [u, tmax] if the segment straddles and it has work
  *   neither                        -> next pending far side from the stack (the second recursive call, :250-252), or done */
 /* returns the child slot the walk continued into (0 front, 1 back), or 2 when it continued from the stack / finished */
-BSPK_HD int32_t lane_node_apply( Lane & l, StackEntry16 * stack, float nx, float ny, float nz, float d, int32_t c0, int32_t c1 ) {
+template< class Stack >
+BSPK_HD int32_t lane_node_apply( Lane & l, const Stack & stack, float nx, float ny, float nz, float d, int32_t c0, int32_t c1 ) {
 	const float denom = dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );                /* :220 */
 	const float dist = -( dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d );        /* :221 */
 	const float u = dist / denom;                                                  /* :227 */
@@ -313,8 +342,7 @@ BSPK_HD int32_t lane_node_apply( Lane & l, StackEntry16 * stack, float nx, float
 	const bool do_pop = !near_ok && !far_work;
 	const bool can_pop = do_pop && l.sp > 0;
 	if( do_push ) {
-		StackEntry16 e; e.node = cf; e.tmin = u; e.tmax = l.tmax; e.pad = 0;
-		stack[ l.sp ] = e;
+		stack_put( stack, l.sp, cf, u, l.tmax );
 		l.sp++;
 	}
 	/* continue into the near child, else the far child; with neither, the next pending far side (or done) */
@@ -324,14 +352,13 @@ BSPK_HD int32_t lane_node_apply( Lane & l, StackEntry16 * stack, float nx, float
 	if( do_pop ) l.cur = kCurDone;
 	if( can_pop ) {
 		l.sp--;
-		const StackEntry16 top = stack[ l.sp ];
-		l.cur = top.node; l.tmin = top.tmin; l.tmax = top.tmax;
+		stack_get( stack, l.sp, l.cur, l.tmin, l.tmax );
 	}
 	return do_pop ? 2 : ( ( near_back == near_ok ) ? 1 : 0 );                      /* near taken: slot near_back; far taken: the other one */
 }
 
-template< class Map >
-BSPK_HD void lane_node_step( const Map & map, Lane & l, StackEntry16 * stack ) {
+template< class Map, class Stack >
+BSPK_HD void lane_node_step( const Map & map, Lane & l, const Stack & stack ) {
 	float nx, ny, nz, d; int32_t c0, c1;
 	map.node( l.cur, nx, ny, nz, d, c0, c1 );
 	lane_node_apply( l, stack, nx, ny, nz, d, c0, c1 );
@@ -348,8 +375,8 @@ BSPK_HD float bits_to_float( uint32_t u ) {
 /* the same step on a QNodeRec (map_layout.h): one record fetch, one or two tree levels.  A packed record's plane is
  * rebuilt as the exact unit normal it stands for and goes through lane_node_apply like any other plane, so the
  * arithmetic -- and the result -- is that of two lane_node_steps; only the second record fetch is gone. */
-template< class Map >
-BSPK_HD void lane_qnode_step( const Map & map, Lane & l, StackEntry16 * stack ) {
+template< class Map, class Stack >
+BSPK_HD void lane_qnode_step( const Map & map, Lane & l, const Stack & stack ) {
 	uint32_t q0, q1, q2, q3, q4, q5, q6, w;
 	map.qnode( l.cur, q0, q1, q2, q3, q4, q5, q6, w );
 	if( !( w & kQPacked ) ) {
@@ -371,8 +398,8 @@ BSPK_HD void lane_qnode_step( const Map & map, Lane & l, StackEntry16 * stack ) 
 }
 
 /* up to `max_steps` node steps; stops early when the lane leaves node mode */
-template< class Map >
-BSPK_HD void lane_node_phase( const Map & map, Lane & l, StackEntry16 * stack, uint32_t max_steps ) {
+template< class Map, class Stack >
+BSPK_HD void lane_node_phase( const Map & map, Lane & l, const Stack & stack, uint32_t max_steps ) {
 	if( !lane_in_node( l ) ) return;
 	for( ; max_steps > 0 && lane_in_node( l ); max_steps-- ) {
 		if constexpr( Map::kPackedNodes ) lane_qnode_step( map, l, stack );
@@ -383,8 +410,8 @@ BSPK_HD void lane_node_phase( const Map & map, Lane & l, StackEntry16 * stack, u
 
 /* up to `max_steps` iterations of trace_seg_brush's side loop (bsp.cc:128-165), moving through the
  * leaf's brushes (trace_seg_leaf, bsp.cc:188-201).  Flatten guarantees every referenced brush has >= 1 side. */
-template< class Map >
-BSPK_HD void lane_leaf_phase( const Map & map, Lane & l, const StackEntry16 * stack, uint32_t max_steps ) {
+template< class Map, class Stack >
+BSPK_HD void lane_leaf_phase( const Map & map, Lane & l, const Stack & stack, uint32_t max_steps ) {
 	/* end = start + dir * tmax (bsp.cc:121); tmax is the leaf interval's and is constant inside a leaf */
 	float ex = l.r.sx + l.r.dx * l.tmax, ey = l.r.sy + l.r.dy * l.tmax, ez = l.r.sz + l.r.dz * l.tmax;
 	for( ; max_steps > 0 && lane_in_leaf( l ); max_steps-- ) {
@@ -435,24 +462,33 @@ BSPK_HD void lane_leaf_phase( const Map & map, Lane & l, const StackEntry16 * st
 		if( l.hflags & kHitFlag ) { l.cur = kCurDone; break; }
 		if( l.sp == 0 ) { l.cur = kCurDone; break; }
 		l.sp--;
-		const StackEntry16 e = stack[ l.sp ];
-		l.cur = e.node; l.tmin = e.tmin; l.tmax = e.tmax;
+		stack_get( stack, l.sp, l.cur, l.tmin, l.tmax );
 		l.s = 0; l.s_end = 0;
 		ex = l.r.sx + l.r.dx * l.tmax; ey = l.r.sy + l.r.dy * l.tmax; ez = l.r.sz + l.r.dz * l.tmax;
 	}
 }
 
-/* trace_one written with the resumable phases (budgets make no difference to the result) */
-template< class Map, int kStack >
+/* trace_one written with the resumable phases (budgets make no difference to the result); kSplit > 0 keeps the
+ * first kSplit stack slots in a separate array, the way the kernels keep them in shared memory */
+template< class Map, int kStack, int kSplit = 0 >
 BSPK_HD void trace_one_phased( const Map & map, float sx, float sy, float sz, float ex, float ey, float ez,
                                uint32_t node_budget, uint32_t side_budget, Ray & r_out, HitState & h_out, const StartGrid * grid = nullptr ) {
 	StackEntry16 stack[ kStack ];
+	StackEntry16 low[ kSplit > 0 ? kSplit : 1 ];
 	Lane l;
 	lane_start( l, sx, sy, sz, ex, ey, ez );
 	if( grid ) lane_start_at( l, grid_start_ref( *grid, sx, sy, sz, ex, ey, ez ) );
 	while( !lane_done( l ) ) {
-		lane_node_phase( map, l, stack, node_budget );
-		lane_leaf_phase( map, l, stack, side_budget );
+		if constexpr( kSplit > 0 ) {
+			SplitStack< kSplit > st; st.lo = low; st.hi = stack;
+			lane_node_phase( map, l, st, node_budget );
+			lane_leaf_phase( map, l, st, side_budget );
+		}
+		else {
+			StackEntry16 * st = stack;
+			lane_node_phase( map, l, st, node_budget );
+			lane_leaf_phase( map, l, st, side_budget );
+		}
 	}
 	r_out = l.r;
 	lane_hit_state( l, h_out );

@@ -400,6 +400,44 @@ __device__ __forceinline__ void lane_load_segment( const TraceParams & p, uint32
 	if( p.grid.cells ) lane_start_at( l, grid_start_ref( p.grid, sx, sy, sz, ex, ey, ez ) );
 }
 
+/* Traversal stack with its first kSlots entries in shared memory.
+ *
+ * Local memory interleaves threads word by word, so a 16-byte entry of one lane is four words in four different
+ * 128-byte lines: a push by k lanes at k different heights costs 4k L1 wavefronts (ncu on city10k long rays: stack
+ * traffic was 48 % of all L1 sectors, and the L1 data pipe the busiest unit at 82 %).  In shared memory, laid out
+ * [slot][thread] with 16 bytes per thread, the bank depends on the thread only: any mix of heights is conflict-free
+ * and a warp-wide push or pop is at most four wavefronts, outside the L1 tag path.  Measured heights:
+ * 87 % of the pushes of long rays land in slots 0-3, 99 % in 0-5; deeper entries overflow to local memory. */
+template< int kSlots, int kStride > struct SmemStack;
+template< int kSlots, int kThreads > struct StackOf { typedef SmemStack< kSlots, kThreads * 16 > type; };
+template< int kThreads > struct StackOf< 0, kThreads > { typedef StackEntry16 * type; };
+
+template< int kSlots, int kStride >
+struct SmemStack {
+	uint32_t base;              /* shared-window byte address of this thread's slot 0; slot i is kStride bytes further */
+	StackEntry16 * overflow;    /* local memory, indexed by the absolute slot number */
+};
+/* (A branch-free form -- predicated STS/LDS plus a predicated local overflow -- measured 6-12 % slower on every
+ * workload: as branches, a warp in which no lane pushes or pops skips the block.) */
+template< int kSlots, int kStride >
+__device__ __forceinline__ void stack_put( const SmemStack< kSlots, kStride > & s, int32_t i, int32_t node, float tmin, float tmax ) {
+	/* both stores name the same four registers, so one register quad serves either destination; the fourth word is padding */
+	uint32_t pad;
+	asm( "" : "=r"( pad ) );
+	asm volatile( "{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %0, %7;\n\t@q st.shared.v4.b32 [%1], {%3,%4,%5,%6};\n\t@!q st.local.v4.b32 [%2], {%3,%4,%5,%6};\n\t}"
+		:: "r"( i ), "r"( s.base + ( uint32_t ) i * ( uint32_t ) kStride ), "l"( __cvta_generic_to_local( s.overflow + i ) ),
+		   "r"( node ), "f"( tmin ), "f"( tmax ), "r"( pad ), "n"( kSlots ) : "memory" );
+}
+template< int kSlots, int kStride >
+__device__ __forceinline__ void stack_get( const SmemStack< kSlots, kStride > & s, int32_t i, int32_t & node, float & tmin, float & tmax ) {
+	if( i < kSlots ) {
+		int32_t pad;
+		asm volatile( "ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"( node ), "=f"( tmin ), "=f"( tmax ), "=r"( pad )
+			: "r"( s.base + ( uint32_t ) i * ( uint32_t ) kStride ) : "memory" );
+	}
+	else stack_get( s.overflow, i, node, tmin, tmax );
+}
+
 /* ---------------------------------------------------------------- K1/K2, phase-scheduled
  *
  * ncu on the round-based kernel above showed it issue-bound (88 % issue-active on rooms8) at
@@ -410,7 +448,7 @@ __device__ __forceinline__ void lane_load_segment( const TraceParams & p, uint32
  * a leaf phase when at least `leaf_threshold` lanes wait in a leaf (or nobody can step nodes),
  * otherwise a node phase.  Lanes of the other kind just keep their registers.  Finished lanes
  * are re-filled as before. */
-template< int kMode, int kStack, int kMaxThreads, int kMinBlocks >
+template< int kMode, int kStack, int kMaxThreads, int kMinBlocks, int kSmemSlots = 0 >
 __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const TraceParams p ) {
 	extern __shared__ __align__( 128 ) unsigned char smem[];
 	__shared__ __align__( 8 ) uint64_t stage_bar;
@@ -430,7 +468,14 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 	lane_start( l, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f );
 	l.cur = kCurIdle;
 	l.brush = -1; l.bflags = 0; l.tfar = l.tnear = 0.0f; l.far_side = -1;
-	StackEntry16 stack[ kStack ];
+	StackEntry16 stack_local[ kStack ];
+	/* kSmemSlots > 0: the first slots live in shared memory, behind whatever this mode staged there */
+	typename StackOf< kSmemSlots, kMaxThreads >::type stack;
+	if constexpr( kSmemSlots > 0 ) {
+		stack.base = opaque_u32( smem_u32( smem ) + ( ( p.staged_bytes + 127u ) & ~127u ) + threadIdx.x * 16u );
+		stack.overflow = stack_local;
+	}
+	else stack = stack_local;
 	uint32_t seg = 0, my_hits = 0;
 
 	for( ;; ) {
@@ -504,7 +549,8 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_simple( const TraceParams
 	map.refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
 	map.sides = reinterpret_cast< const SideRec * >( p.image + p.off_sides );
 	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
-	StackEntry16 stack[ kStack ];
+	StackEntry16 stack_local[ kStack ];
+	StackEntry16 * const stack = stack_local;
 	uint32_t my_hits = 0;
 	for( uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x; seg < p.n; seg += gridDim.x * blockDim.x ) {
 		Lane l;

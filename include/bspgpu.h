@@ -114,6 +114,9 @@ enum {
 	BSPGPU_OPT_MAX_LAUNCH_SEGMENTS = 12, /* segments per kernel launch, default and maximum 2^30 (in-kernel indices are 32-bit) */
 	BSPGPU_OPT_START_GRID = 13,     /* segments whose endpoints share a start-grid cell begin below the root (bit-identical, see map_layout.h):
 	                                   1 on, 0 off (always node 0), -1 (default) on unless the map is staged in shared memory */
+	BSPGPU_OPT_SMEM_STACK = 15,     /* GLOBAL variant with 256-thread CTAs: keep the first N (0, 2, 4, 6, 8) traversal-stack entries of every
+	                                   thread in shared memory instead of local memory (deeper entries overflow to local memory);
+	                                   -1 (default) = 6.  Bit-identical; +17 % on long rays (profiles/README.md) */
 	BSPGPU_OPT_PACKED_NODES = 14    /* GLOBAL variant: walk two-level node records (one gather covers a node and both children when their
 	                                   planes are axis-aligned; bit-identical, see map_layout.h): 1 on, 0 (default) off -- halves the
 	                                   record fetches but measured slower on B200 (the step is instruction-bound), see profiles/README.md */

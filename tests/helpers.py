@@ -109,7 +109,7 @@ class HostSim:
         return dict(zip(("nodes", "refs", "sides", "depth", "staged_bytes", "total_bytes", "grid_cells", "packed_nodes", "expanded_children"),
                         (int(v) for v in out)))
 
-    def trace(self, segs, budgets=None, grid=False, packed=False):
+    def trace(self, segs, budgets=None, grid=False, packed=False, split_stack=False):
         from bsp_b200.api import RESULT_DT
         segs = np.ascontiguousarray(segs, np.float32)
         res = np.zeros(len(segs), RESULT_DT)
@@ -117,7 +117,7 @@ class HostSim:
         if budgets is None:
             self.l.hostsim_trace(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data)
         else:
-            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], (1 if grid else 0) | (2 if packed else 0))
+            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], (1 if grid else 0) | (2 if packed else 0) | (4 if split_stack else 0))
         return res, pos
 
     def leaf(self, pts):

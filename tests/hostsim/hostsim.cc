@@ -131,9 +131,11 @@ void hostsim_trace_phased( void * h, const float * segs, uint64_t stride, uint64
 		Ray r; HitState hs;
 		const uint32_t nb = node_budget ? node_budget : 1 + ( uint32_t ) ( i % 7 );
 		const uint32_t sb = side_budget ? side_budget : 1 + ( uint32_t ) ( ( i / 7 ) % 5 );
-		/* use_grid: bit 0 = start grid, bit 1 = walk the packed two-level records (QNodeRec) */
+		/* use_grid: bit 0 = start grid, bit 1 = walk the packed two-level records (QNodeRec),
+		 * bit 2 = first two stack slots in a separate array (the model of the kernels' shared-memory stack) */
 		const StartGrid * grid = ( use_grid & 1 ) ? &s->grid : nullptr;
-		if( use_grid & 2 ) trace_one_phased< ImageMapPacked, 64 >( s->packed, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
+		if( use_grid & 4 ) trace_one_phased< ImageMap, 64, 2 >( s->view, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
+		else if( use_grid & 2 ) trace_one_phased< ImageMapPacked, 64 >( s->packed, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
 		else trace_one_phased< ImageMap, 64 >( s->view, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
 		if( out ) out[ i ] = make_result( hs, s->side_plane );
 		if( pos4 ) {

@@ -471,3 +471,23 @@ def test_packed_nodes(native, maps, oracle_mod, name):
         res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
         _compare(res, pos, exp, exp_pos, f"{name} packed {packed} grid {grid} steps {steps}")
     g.close()
+
+
+@pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k", "tilted", "mega200k"])
+def test_smem_stack(native, maps, oracle_mod, name):
+    """BSPGPU_OPT_SMEM_STACK: the first 2..8 traversal-stack slots of every thread in shared memory, deeper ones in local
+    memory -- same bits as the all-local stack (2 slots: most pushes overflow; tilted is 42 levels deep)."""
+    from tools import mapgen, seggen
+    m, _ = maps(name)
+    lo, hi = mapgen.seg_bounds(m)
+    segs = np.vstack((_segments(m, 50_000, 30_000, 150_000, 4096), seggen.long_rays(81, 0, 300_000, lo, hi, 0.01, 8.0)))
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    g.set_option(1, 3)
+    for slots, steps in ((2, 8), (4, 1), (6, 8), (8, 3), (0, 8)):
+        g.set_option(15, slots); g.set_option(7, steps)
+        pos = np.zeros((len(segs), 4), np.float32)
+        res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+        assert g.info()["smem_bytes"] == slots * 256 * 16
+        _compare(res, pos, exp, exp_pos, f"{name} smem stack {slots} steps {steps}")
+    g.close()

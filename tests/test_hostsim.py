@@ -141,6 +141,20 @@ def test_packed_nodes_are_bit_identical(oracle_mod, maps, name):
         _check(res, pos, exp, exp_pos, f"{name} packed nodes, grid {grid}")
 
 
+@pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k", "tilted"])
+def test_split_stack_is_bit_identical(oracle_mod, maps, name):
+    """the kernels may keep the first traversal-stack slots in shared memory and the rest in local memory
+    (trace_kernels.cuh: SmemStack); the host model splits after two slots so both halves and the hand-over are used."""
+    from tools import mapgen, seggen
+    m, _ = maps(name)
+    sim = HostSim(m)
+    lo, hi = mapgen.seg_bounds(m)
+    segs = np.vstack((mixed_segments(m, 50_000, 30_000, 100_000, 4096), seggen.long_rays(80, 0, 150_000, lo, hi, 0.01, 8.0)))
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    res, pos = sim.trace(segs, (0, 0), grid=sim.layout()["grid_cells"] > 0, split_stack=True)
+    _check(res, pos, exp, exp_pos, f"{name} split stack")
+
+
 def test_packed_nodes_only_for_exact_positive_unit_normals(maps):
     """-1 / -0 / almost-unit normals must stay general records (the kernel rebuilds +unit normals only)"""
     import copy

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--sched", default="0")
     ap.add_argument("--side_steps", default="8")
     ap.add_argument("--leaf_thr", default="12")
+    ap.add_argument("--packed", type=int, default=0, help="BSPGPU_OPT_PACKED_NODES")
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     bsp_b200.build()
@@ -39,6 +40,7 @@ def main():
     diag = float(np.sqrt(((hi - lo).astype(np.float64) ** 2).sum()))
     g = bsp_b200.BspGpu(path, 0)
     g.set_stream(torch.cuda.current_stream().cuda_stream)
+    g.set_option(14, a.packed)
     segs = torch.empty((a.n, 8), dtype=torch.float32, device="cuda")
     if a.kind == "uniform":
         g.generate(segs, 0, a.n, 0, 2, lo, hi)
