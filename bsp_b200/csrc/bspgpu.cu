@@ -89,8 +89,18 @@ TraceKernel pick_smem_stack( int slots ) {
 		default: return trace_phased< kGlobal, S, 256, 5, 8 >;
 	}
 }
+/* same with the whole map staged and one 1024-thread CTA per SM */
+template< int S >
+TraceKernel pick_smem_stack_staged( int slots ) {
+	switch( slots ) {
+		case 2: return trace_phased< kSmemAll, S, 1024, 1, 2 >;
+		case 4: return trace_phased< kSmemAll, S, 1024, 1, 4 >;
+		default: return trace_phased< kSmemAll, S, 1024, 1, 6 >;
+	}
+}
 TraceKernel pick_kernel( int mode, int depth, int threads, int sched, int smem_stack ) {
 	if( sched == 4 ) return pick_simple( depth, threads );
+	if( smem_stack > 0 && mode == kSmemAll ) return depth <= 32 ? pick_smem_stack_staged< 32 >( smem_stack ) : pick_smem_stack_staged< 64 >( smem_stack );
 	if( smem_stack > 0 ) return depth <= 32 ? pick_smem_stack< 32 >( smem_stack ) : pick_smem_stack< 64 >( smem_stack );
 	switch( mode ) {
 		case kSmemAll: return pick_stack< kSmemAll >( depth, threads, sched );
@@ -184,6 +194,13 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 		if( mode == kGlobal && h->opt_sched == 0 && threads <= 256 && want_stack > 0 ) {
 			smem_stack = want_stack <= 2 ? 2 : ( want_stack <= 4 ? 4 : ( want_stack <= 6 ? 6 : 8 ) );
 			smem += ( uint32_t ) smem_stack * 256u * 16u;
+		}
+		else if( mode == kSmemAll && h->opt_sched == 0 && threads > 512 && h->opt_smem_stack > 0 ) {
+			/* behind the staged map, as many slots as still fit (explicit request only: measured in profiles/README.md) */
+			smem = ( smem + 127u ) & ~127u;
+			smem_stack = h->opt_smem_stack <= 2 ? 2 : ( h->opt_smem_stack <= 4 ? 4 : 6 );
+			while( smem_stack > 0 && ( uint64_t ) smem + ( uint64_t ) smem_stack * 1024u * 16u > ( uint64_t ) h->max_smem_optin ) smem_stack -= 2;
+			smem += ( uint32_t ) smem_stack * 1024u * 16u;
 		}
 		TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched, smem_stack );
 		CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );

@@ -490,4 +490,13 @@ def test_smem_stack(native, maps, oracle_mod, name):
         res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
         assert g.info()["smem_bytes"] == slots * 256 * 16
         _compare(res, pos, exp, exp_pos, f"{name} smem stack {slots} steps {steps}")
+    if g.info()["staged_bytes"] < 140 * 1024:
+        # the same behind a staged map (SMEM variant, one 1024-thread CTA per SM); explicit request only
+        g.set_option(1, 1)
+        for slots in (2, 6):
+            g.set_option(15, slots)
+            pos = np.zeros((len(segs), 4), np.float32)
+            res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+            assert g.info()["variant"] == 1 and g.info()["smem_bytes"] > g.info()["staged_bytes"]
+            _compare(res, pos, exp, exp_pos, f"{name} staged map + smem stack {slots}")
     g.close()
