@@ -126,7 +126,7 @@ struct bspgpu {
 	/* options */
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 96 * 1024;
 	int64_t opt_chunk = 2ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;   /* 0 = per-variant default */
-	int64_t opt_sched = 0, opt_side_steps = 6, opt_leaf_threshold = 16;
+	int64_t opt_sched = 0, opt_side_steps = 3, opt_leaf_threshold = 16;
 	int64_t opt_smem_stack = -1;   /* GLOBAL variant, 256-thread CTAs: traversal-stack slots per thread kept in shared memory (0, 2, 4, 6, 8; -1 auto = 6) */
 	int64_t opt_packed_nodes = 0;  /* 1: two-level node records on the read-only path (measured slower, profiles/README.md; kept as a tested option) */
 	int64_t opt_start_grid = -1;   /* -1 auto: on unless the whole map sits in shared memory (there a node step is cheaper than the grid's global load) */

@@ -110,6 +110,32 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 		}
 	}
 
+	/* ---- sides, re-laid out per solid brush so that every brush starts at an even index and has an even count:
+	 *      the kernels fetch and clip TWO sides per step (one 32-byte gather).  Padding sides have a zero normal and
+	 *      d = +inf: dot(p, 0) is 0 or NaN, so start_dist and end_dist are -inf or NaN for ANY input -- never > 0 (no
+	 *      reject, bsp.cc:135), never >= 0 (not entering: `starts_inside` kept, :139), and a crossing parameter of
+	 *      +inf or NaN is out of every range (:144).  (d = 0 is not enough: a finite start with an infinite end gives
+	 *      start_dist = 0, end_dist = NaN, i.e. a crossing that "enters".)  A solid brush WITHOUT sides (the reference's
+	 *      loop, :127, does not run: never hits, `starts_inside` stays true) becomes one such pair. */
+	std::vector< uint32_t > new_first( L.num_brushes, 0 ), new_count( L.num_brushes, 0 );
+	std::vector< SideRec > osides;
+	std::vector< uint32_t > oside_plane;
+	for( uint32_t b = 0; b < L.num_brushes; b++ ) {
+		if( !brush_solid[ b ] ) continue;
+		new_first[ b ] = ( uint32_t ) osides.size();
+		for( uint32_t k = 0; k < brushes[ b ].num_sides; k++ ) {
+			const uint32_t pi = sides[ brushes[ b ].first_side + k ].plane;
+			SideRec r; r.nx = planes[ pi ].n[ 0 ]; r.ny = planes[ pi ].n[ 1 ]; r.nz = planes[ pi ].n[ 2 ]; r.d = planes[ pi ].d;
+			osides.push_back( r ); oside_plane.push_back( pi );
+		}
+		while( osides.size() == new_first[ b ] || ( osides.size() & 1 ) ) {
+			SideRec z; z.nx = z.ny = z.nz = 0.0f; z.d = INFINITY;
+			osides.push_back( z ); oside_plane.push_back( 0 );
+		}
+		new_count[ b ] = ( uint32_t ) osides.size() - new_first[ b ];
+		if( osides.size() >= 0x7ffffff0u ) { err = "too many brush sides"; return BSPGPU_E_MAP; }
+	}
+
 	/* ---- emit */
 	const uint32_t num_nodes = ( uint32_t ) order.size();
 	std::vector< NodeRec > onodes( num_nodes );
@@ -129,12 +155,7 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 				const uint32_t b = leaf_brushes[ lf.first_brush + j ];
 				if( !brush_solid[ b ] ) continue;
 				BrushRef r;
-				r.first_side = brushes[ b ].first_side; r.num_sides = brushes[ b ].num_sides;
-				/* a solid brush without sides: the reference's side loop (bsp.cc:127) does not run, the brush
-				 * never hits and `starts_inside` stays true.  One synthetic side with a zero normal and d = 0
-				 * (appended after the file's sides) does exactly that: start_dist and end_dist are 0 (or NaN for
-				 * non-finite input), so the side is skipped or crosses out of range -- no hit, inside kept. */
-				if( r.num_sides == 0 ) { r.first_side = L.num_brush_sides; r.num_sides = 1; }
+				r.first_side = new_first[ b ]; r.num_sides = new_count[ b ];   /* even start, even count (see above) */
 				r.brush = ( int32_t ) b; r.reserved = 0;
 				orefs.push_back( r );
 			}
@@ -146,7 +167,7 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	}
 
 	MapImageLayout & lay = out.layout;
-	const uint32_t num_sides_out = L.num_brush_sides + 1;   /* + the synthetic zero side */
+	const uint32_t num_sides_out = ( uint32_t ) osides.size();
 	lay.num_nodes = num_nodes; lay.num_refs = ( uint32_t ) orefs.size(); lay.num_sides = num_sides_out;
 	lay.tree_depth = tree_depth;
 	lay.off_nodes = 0;
@@ -285,15 +306,10 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	memcpy( out.image.data() + lay.off_nodes, onodes.data(), onodes.size() * sizeof( NodeRec ) );
 	if( !orefs.empty() ) memcpy( out.image.data() + lay.off_refs, orefs.data(), orefs.size() * sizeof( BrushRef ) );
 	memcpy( out.image.data() + lay.off_qnodes, qnodes.data(), qnodes.size() * sizeof( QNodeRec ) );
-	SideRec * osides = ( SideRec * ) ( out.image.data() + lay.off_sides );
-	uint32_t * oside_plane = ( uint32_t * ) ( out.image.data() + lay.off_side_plane );
-	for( uint32_t s = 0; s < L.num_brush_sides; s++ ) {
-		const DiskPlane & pl = planes[ sides[ s ].plane ];
-		osides[ s ].nx = pl.n[ 0 ]; osides[ s ].ny = pl.n[ 1 ]; osides[ s ].nz = pl.n[ 2 ]; osides[ s ].d = pl.d;
-		oside_plane[ s ] = sides[ s ].plane;
+	if( !osides.empty() ) {
+		memcpy( out.image.data() + lay.off_sides, osides.data(), osides.size() * sizeof( SideRec ) );
+		memcpy( out.image.data() + lay.off_side_plane, oside_plane.data(), oside_plane.size() * sizeof( uint32_t ) );
 	}
-	osides[ L.num_brush_sides ].nx = osides[ L.num_brush_sides ].ny = osides[ L.num_brush_sides ].nz = osides[ L.num_brush_sides ].d = 0.0f;
-	oside_plane[ L.num_brush_sides ] = 0;
 	if( !grid_cells.empty() ) memcpy( out.image.data() + lay.off_grid, grid_cells.data(), grid_cells.size() * sizeof( int32_t ) );
 	return BSPGPU_OK;
 }

@@ -408,6 +408,27 @@ BSPK_HD void lane_node_phase( const Map & map, Lane & l, const Stack & stack, ui
 	l.s = 0; l.s_end = 0;                                                          /* if the walk reached a leaf: fetch its first brush reference */
 }
 
+/* one turn of trace_seg_brush's side loop (bsp.cc:128-165) for side `index` with plane (n, d); `live` = false leaves the
+ * lane untouched.  Returns whether the side rejected the brush (:135). */
+BSPK_HD bool lane_side_apply( Lane & l, float ex, float ey, float ez, int32_t index, bool live, float nx, float ny, float nz, float d ) {
+	const float start_dist = dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d;    /* :131 */
+	const float end_dist = dot3( ex, ey, ez, nx, ny, nz ) - d;                  /* :132 */
+	const float denom = -dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );           /* :141 */
+	const float t = start_dist / denom;                                         /* :142 */
+	const bool rejected = live && start_dist > 0.0f && end_dist > 0.0f;         /* :135 */
+	const bool behind = start_dist <= 0.0f && end_dist <= 0.0f;                 /* :137 */
+	const bool crossing = live && !rejected && !behind;
+	const bool entering = start_dist >= 0.0f;
+	const bool in_range = crossing && t >= l.tmin && t <= l.tmax;               /* :144 */
+	const bool raise_far = in_range && entering && t >= l.tfar;                 /* :147-148 */
+	const bool lower_near = in_range && !entering && t <= l.tnear;              /* :154 */
+	if( crossing && entering ) l.bflags &= ~kBrushInside;                       /* :139 */
+	if( raise_far ) { l.tfar = t; l.far_side = index; }
+	if( lower_near ) l.tnear = t;
+	if( raise_far || lower_near ) l.bflags |= kBrushHit;
+	return rejected;
+}
+
 /* up to `max_steps` iterations of trace_seg_brush's side loop (bsp.cc:128-165), moving through the
  * leaf's brushes (trace_seg_leaf, bsp.cc:188-201).  Flatten guarantees every referenced brush has >= 1 side. */
 template< class Map, class Stack >
@@ -423,24 +444,14 @@ BSPK_HD void lane_leaf_phase( const Map & map, Lane & l, const Stack & stack, ui
 			l.bflags = kBrushInside | ( ( nraw & kLastRef ) ? kBrushLastRef : 0u );
 			l.tfar = l.tmin; l.tnear = l.tmax; l.far_side = -1;
 		}
-		float nx, ny, nz, d;
-		map.side( l.s, nx, ny, nz, d );
-		const float start_dist = dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d;    /* :131 */
-		const float end_dist = dot3( ex, ey, ez, nx, ny, nz ) - d;                  /* :132 */
-		const float denom = -dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );           /* :141 */
-		const float t = start_dist / denom;                                         /* :142 */
-		const bool rejected = start_dist > 0.0f && end_dist > 0.0f;                 /* :135 */
-		const bool behind = start_dist <= 0.0f && end_dist <= 0.0f;                 /* :137 */
-		const bool crossing = !rejected && !behind;
-		const bool entering = start_dist >= 0.0f;
-		const bool in_range = crossing && t >= l.tmin && t <= l.tmax;               /* :144 */
-		const bool raise_far = in_range && entering && t >= l.tfar;                 /* :147-148 */
-		const bool lower_near = in_range && !entering && t <= l.tnear;              /* :154 */
-		if( crossing && entering ) l.bflags &= ~kBrushInside;                       /* :139 */
-		if( raise_far ) { l.tfar = t; l.far_side = ( int32_t ) l.s; }
-		if( lower_near ) l.tnear = t;
-		if( raise_far || lower_near ) l.bflags |= kBrushHit;
-		l.s++;
+		/* two sides per step: flatten starts every brush at an even side index with an even count (zero-normal padding
+		 * sides change nothing), so sides s and s+1 arrive in one 32-byte fetch.  They are clipped in order; the second
+		 * one only if the first did not reject the brush, exactly like two turns of the reference's loop. */
+		float n0x, n0y, n0z, d0, n1x, n1y, n1z, d1;
+		map.side_pair( l.s, n0x, n0y, n0z, d0, n1x, n1y, n1z, d1 );
+		bool rejected = lane_side_apply( l, ex, ey, ez, ( int32_t ) l.s, true, n0x, n0y, n0z, d0 );
+		rejected = lane_side_apply( l, ex, ey, ez, ( int32_t ) l.s + 1, !rejected, n1x, n1y, n1z, d1 ) || rejected;
+		l.s += 2;
 		if( !rejected && l.s != l.s_end ) continue;
 
 		/* ---- brush over (rejected, or side loop complete): bsp.cc:169-182 folded into :197-200 */
@@ -556,6 +567,10 @@ struct ImageMap {
 	BSPK_HD void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const {
 		const SideRec & s = sides[ i ];
 		nx = s.nx; ny = s.ny; nz = s.nz; d = s.d;
+	}
+	BSPK_HD void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
+		side( i, n0x, n0y, n0z, d0 );
+		side( i + 1, n1x, n1y, n1z, d1 );
 	}
 };
 

@@ -151,6 +151,11 @@ struct SmemAllMap {
 		const float4 p = lds128( sides + ( i << 4 ) );
 		nx = p.x; ny = p.y; nz = p.z; d = p.w;
 	}
+	__device__ __forceinline__ void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
+		const uint32_t a = sides + ( i << 4 );
+		const float4 p = lds128( a ), q = lds128( a + 16 );
+		n0x = p.x; n0y = p.y; n0z = p.z; d0 = p.w; n1x = q.x; n1y = q.y; n1z = q.z; d1 = q.w;
+	}
 };
 
 /* one 256-bit read-only load (sm_100: LDG.E.ENL2.256.CONSTANT) fetches a whole 32-byte NodeRec --
@@ -159,6 +164,12 @@ struct SmemAllMap {
 __device__ __forceinline__ void ldg256( const void * p, float & a, float & b, float & c, float & d, int32_t & e, int32_t & f, int32_t & g, int32_t & h ) {
 	asm volatile( "ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=f"( a ), "=f"( b ), "=f"( c ), "=f"( d ), "=r"( e ), "=r"( f ), "=r"( g ), "=r"( h ) : "l"( p ) );
+}
+
+/* two consecutive SideRecs (i even: 32-byte aligned) in one 256-bit read-only load */
+__device__ __forceinline__ void ldg_side_pair( const SideRec * p, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) {
+	asm volatile( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"( n0x ), "=f"( n0y ), "=f"( n0z ), "=f"( d0 ), "=f"( n1x ), "=f"( n1y ), "=f"( n1z ), "=f"( d1 ) : "l"( p ) );
 }
 
 struct GlobalMap {
@@ -179,6 +190,9 @@ struct GlobalMap {
 		const float4 p = __ldg( reinterpret_cast< const float4 * >( &sides[ i ] ) );
 		nx = p.x; ny = p.y; nz = p.z; d = p.w;
 	}
+	__device__ __forceinline__ void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
+		ldg_side_pair( &sides[ i ], n0x, n0y, n0z, d0, n1x, n1y, n1z, d1 );
+	}
 };
 
 /* kGlobalPacked: the walk fetches two-level QNodeRecs (map_layout.h) -- still one 256-bit gather per fetch, about half
@@ -198,6 +212,9 @@ struct GlobalPackedMap {
 		const float4 p = __ldg( reinterpret_cast< const float4 * >( &sides[ i ] ) );
 		nx = p.x; ny = p.y; nz = p.z; d = p.w;
 	}
+	__device__ __forceinline__ void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
+		ldg_side_pair( &sides[ i ], n0x, n0y, n0z, d0, n1x, n1y, n1z, d1 );
+	}
 };
 
 struct SmemTopMap {
@@ -216,6 +233,9 @@ struct SmemTopMap {
 	}
 	__device__ __forceinline__ void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const { g.ref( i, first, nraw, brush ); }
 	__device__ __forceinline__ void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const { g.side( i, nx, ny, nz, d ); }
+	__device__ __forceinline__ void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
+		g.side_pair( i, n0x, n0y, n0z, d0, n1x, n1y, n1z, d1 );
+	}
 };
 
 template< int kMode > struct MapOf;

@@ -109,7 +109,7 @@ enum {
 	BSPGPU_OPT_SCHEDULER = 9,       /* 0 = phase-scheduled lanes (default), 1 = round-based while-while kernel,
 	                                   2 = phase-scheduled at <= 40 registers (1536 threads/SM), 3 = two segments per lane (experimental),
 	                                   4 = one thread per segment, no scheduling (GLOBAL only; for very short walks) */
-	BSPGPU_OPT_SIDE_STEPS = 10,     /* brush-side steps a lane takes per leaf phase */
+	BSPGPU_OPT_SIDE_STEPS = 10,     /* side steps a lane takes per leaf phase; one step clips two brush sides (default 3) */
 	BSPGPU_OPT_LEAF_THRESHOLD = 11, /* lanes waiting in a leaf that make a warp run a leaf phase (1..32) */
 	BSPGPU_OPT_MAX_LAUNCH_SEGMENTS = 12, /* segments per kernel launch, default and maximum 2^30 (in-kernel indices are 32-bit) */
 	BSPGPU_OPT_START_GRID = 13,     /* segments whose endpoints share a start-grid cell begin below the root (bit-identical, see map_layout.h):

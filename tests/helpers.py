@@ -64,6 +64,18 @@ def grid_adversarial_segments(m, n, seed=5):
     return segs
 
 
+def extreme_segments(n, extent, seed=11):
+    """uniform segments in [-extent, extent]^3; every third one gets 1-3 special coordinates (inf, NaN, huge, denormal, +-0)"""
+    rs = np.random.Generator(np.random.PCG64(seed))
+    segs = np.zeros((n, 8), np.float32)
+    segs[:, 0:3] = rs.uniform(-extent, extent, (n, 3)); segs[:, 4:7] = rs.uniform(-extent, extent, (n, 3))
+    specials = np.array([np.inf, -np.inf, 3.0e38, -3.0e38, 1.0e-40, -1.0e-40, 1.0e-45, 0.0, -0.0, np.nan, 1.0e30, -1.0e30], np.float32)
+    for k in range(0, n, 3):
+        for _ in range(int(rs.integers(1, 4))):
+            segs[k, int(rs.choice([0, 1, 2, 4, 5, 6]))] = specials[int(rs.integers(0, len(specials)))]
+    return segs
+
+
 class HostSim:
     """tests/hostsim: a g++ build of bsp_b200/csrc/trace_core.h + flatten.cc (test-only)."""
 

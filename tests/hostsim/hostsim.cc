@@ -36,6 +36,9 @@ struct CountingMap {
 	void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const { nodes++; m.node( i, nx, ny, nz, d, c0, c1 ); }
 	void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const { refs++; m.ref( i, first, nraw, brush ); }
 	void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const { sides++; m.side( i, nx, ny, nz, d ); }
+	void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
+		sides++; m.side_pair( i, n0x, n0y, n0z, d0, n1x, n1y, n1z, d1 );
+	}
 };
 
 struct CountingMapPacked {
@@ -45,6 +48,9 @@ struct CountingMapPacked {
 	void qnode( int32_t i, uint32_t & q0, uint32_t & q1, uint32_t & q2, uint32_t & q3, uint32_t & q4, uint32_t & q5, uint32_t & q6, uint32_t & w ) const { nodes++; m.qnode( i, q0, q1, q2, q3, q4, q5, q6, w ); }
 	void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const { refs++; m.ref( i, first, nraw, brush ); }
 	void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const { sides++; m.side( i, nx, ny, nz, d ); }
+	void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
+		sides++; m.side_pair( i, n0x, n0y, n0z, d0, n1x, n1y, n1z, d1 );
+	}
 };
 
 extern "C" {

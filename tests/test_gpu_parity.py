@@ -376,15 +376,10 @@ def test_extreme_float_inputs(native, maps, oracle_mod):
     """huge / infinite / denormal / NaN coordinates: the reference just lets IEEE arithmetic run (NaN falls
     out of every comparison), and so must the kernels.  Result records must still agree bit for bit; `pos`
     is compared value-wise with NaN == NaN because NaN payloads differ between SSE and the GPU."""
+    from helpers import extreme_segments
     m, _ = maps("rooms8")
-    rs = np.random.Generator(np.random.PCG64(11))
     n = 60_000
-    segs = np.zeros((n, 8), np.float32)
-    segs[:, 0:3] = rs.uniform(-2048, 2048, (n, 3)); segs[:, 4:7] = rs.uniform(-2048, 2048, (n, 3))
-    specials = np.array([np.inf, -np.inf, 3.0e38, -3.0e38, 1.0e-40, -1.0e-40, 1.0e-45, 0.0, -0.0, np.nan, 1.0e30, -1.0e30], np.float32)
-    for k in range(0, n, 3):                                   # every third segment gets 1-3 special coordinates
-        for _ in range(int(rs.integers(1, 4))):
-            segs[k, int(rs.choice([0, 1, 2, 4, 5, 6]))] = specials[int(rs.integers(0, len(specials)))]
+    segs = extreme_segments(n, 2048)
     with np.errstate(all="ignore"):
         exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
     g = native.BspGpu(m)

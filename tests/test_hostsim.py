@@ -4,7 +4,7 @@ node/leaf phases the persistent kernel runs -- bit for bit, without a GPU."""
 import numpy as np
 import pytest
 
-from helpers import HostSim, bits, grid_adversarial_segments, load_golden, mixed_segments
+from helpers import HostSim, bits, extreme_segments, grid_adversarial_segments, load_golden, mixed_segments
 
 
 def _check(res, pos, exp, exp_pos, what):
@@ -73,6 +73,21 @@ def test_odd_maps(oracle_mod):
     for budgets in (None, (0, 0), (1, 1)):
         res, pos = sim.trace(segs, budgets)
         _check(res, pos, exp, exp_pos, f"odd map {budgets}")
+
+
+@pytest.mark.parametrize("name", ["rooms8", "tilted", "odd"])
+def test_extreme_float_inputs_core(oracle_mod, maps, name):
+    """inf / NaN / huge / denormal coordinates: result records agree bit for bit (NaN falls out of every comparison in the
+    reference, and must here -- in particular at the zero-normal padding sides flatten adds to make side counts even,
+    and at the side-less solid brush of the odd map)."""
+    m = _odd_map() if name == "odd" else maps(name)[0]
+    segs = extreme_segments(90_000, 80 if name == "odd" else 2048)
+    with np.errstate(all="ignore"):
+        exp, _, _ = oracle_mod.Port(m).trace(segs)
+    sim = HostSim(m)
+    for budgets, kw in ((None, {}), ((0, 0), {}), ((0, 0), {"packed": True}), ((0, 0), {"split_stack": True, "grid": sim.layout()["grid_cells"] > 0})):
+        res, _ = sim.trace(segs, budgets, **kw)
+        assert np.array_equal(res.view(np.uint32), exp.view(np.uint32)), f"{name} {budgets} {kw}"
 
 
 def test_position_to_leaf_core(oracle_mod, maps):

@@ -1,6 +1,6 @@
 """Differential fuzzing on the GPU: many seeded maps (axial kd trees and q3map-style tilted trees),
 many segment families (mixed, short, start-grid adversarial, extreme floats), every staging variant,
-start grid on and off -- each result record compared bit for bit with the oracle port.
+start grid on and off, random phase budgets / shared-memory stack slots / packed node records -- each result record compared bit for bit with the oracle port.
     python tools/fuzz_parity.py --seeds 20
 """
 import argparse
@@ -48,6 +48,7 @@ def main():
                         g.set_option(1, variant); g.set_option(13, grid); g.set_option(9, sched)
                         g.set_option(6, int(rs.integers(1, 33))); g.set_option(7, int(rs.integers(1, 40))); g.set_option(10, int(rs.integers(1, 40)))
                         g.set_option(11, int(rs.integers(1, 33)))
+                        g.set_option(15, int(rs.choice([0, 2, 4, 6, 8, -1]))); g.set_option(14, int(rs.integers(0, 2)))   # smem stack slots, packed nodes
                         res = g.trace(segs)
                         bad = int((res.view(np.uint32).reshape(-1, 4) != exp.view(np.uint32).reshape(-1, 4)).any(axis=1).sum())
                         total += len(segs); bad_total += bad

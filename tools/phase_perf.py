@@ -11,7 +11,7 @@ for wl in ("city10k-long", "mega200k-short", "city10k-camera", "rooms8-uniform")
     segs = torch.empty((n, 8), dtype=torch.float32, device="cuda"); out = torch.empty((n, 4), dtype=torch.int32, device="cuda")
     bench.device_segments(g, w, segs, 0, n)
     line = [wl]
-    for steps, side, thr in ((0, 8, 16), (8, 6, 16), (12, 6, 16), (12, 8, 16), (16, 6, 16), (12, 6, 20), (12, 4, 16)):
+    for steps, side, thr in ((0, 6, 16), (0, 2, 16), (0, 3, 16), (0, 4, 16), (0, 5, 16), (0, 3, 12), (0, 4, 20), (12, 3, 16)):
         g.set_option(7, steps); g.set_option(10, side); g.set_option(11, thr)
         g.trace(segs, out=out); best = 1e9
         for _ in range(4):
