@@ -199,7 +199,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, b
 			/* behind the staged map, as many slots as still fit (explicit request only: measured in profiles/README.md) */
 			smem = ( smem + 127u ) & ~127u;
 			smem_stack = h->opt_smem_stack <= 2 ? 2 : ( h->opt_smem_stack <= 4 ? 4 : 6 );
-			while( smem_stack > 0 && ( uint64_t ) smem + ( uint64_t ) smem_stack * 1024u * 16u > ( uint64_t ) h->max_smem_optin ) smem_stack -= 2;
+			while( smem_stack > 0 && ( uint64_t ) smem + ( uint64_t ) smem_stack * 1024u * 16u > smem_cap ) smem_stack -= 2;   /* smem_cap leaves room for static shared memory */
 			smem += ( uint32_t ) smem_stack * 1024u * 16u;
 		}
 		TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched, smem_stack );
