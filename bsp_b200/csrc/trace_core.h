@@ -14,7 +14,8 @@
  * single IEEE-754 rounding in the reference's order: build with -fmad=false -prec-div=true
  * -ftz=false (nvcc) / -ffp-contract=off (g++).  glm::dot(vec3) is (x*x' + y*y') + z*z'.
  *
- * Stack invariant (lets an entry be 8 bytes): the reference's far call gets [t, tmax] where
+ * Stack invariant of the simple form trace_one (lets an entry be 8 bytes; the resumable form the shipped kernel
+ * runs stores its intervals explicitly, see below): the reference's far call gets [t, tmax] where
  * tmax is the interval end of the node that straddled (bsp.cc:250-252).  At any moment the
  * current interval end equals the start (`t`) of the entry on top of the stack, or 1.0f when
  * the stack is empty -- so `tmax` is not stored, it is read back from the entry below on pop.

@@ -8,7 +8,10 @@
  * one.  The per-lane arithmetic is trace_core.h (the reference's statements, one rounding each).
  *
  *   trace_phased      THE SHIPPED KERNEL.  Lanes are resumable node/leaf state machines; each warp
- *                     iteration runs the one bounded phase most of its lanes wait for.
+ *                     iteration runs the one bounded phase most of its lanes wait for.  A node step is one
+ *                     32-byte gather + one plane test, a leaf step one 32-byte gather + two brush sides;
+ *                     with the map in global memory the first traversal-stack slots of every thread live
+ *                     in shared memory (SmemStack below).
  *   trace_persistent  the first version (rounds: every lane descends to a leaf, then every lane
  *                     clips its leaf).  Kept selectable (BSPGPU_OPT_SCHEDULER=1) as a cross-check.
  *   trace_dual        experiment (BSPGPU_OPT_SCHEDULER=3): two segments per lane, one parked in
@@ -20,6 +23,7 @@
  *   kSmemTop : only the first `top_nodes` breadth-first nodes are staged; the rest of the map is
  *              read through the read-only path (L1 -> L2)
  *   kGlobal  : nothing staged; a node is one 256-bit read-only load                      (C3-C5)
+ *   kGlobalPacked : kGlobal over two-level node records (QNodeRec, map_layout.h); a measured-slower option
  * K3  hit count: per-lane counters, one shuffle reduction + one atomicAdd per warp.
  * N3  leaf_kernel: batched BSP::position_to_leaf (reference bsp.cc:273-286).
  *
