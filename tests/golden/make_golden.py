@@ -45,7 +45,30 @@ def main():
         out = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(out, bsp=np.frombuffer(ibsp.to_bytes(m), np.uint8), segs=segs, hit=r["hit"], t=r["t"], pos=r["pos"])
         print(name, len(segs), "segments,", int(r["hit"].sum()), "hits ->", out, os.path.getsize(out), "bytes")
+    extreme()
+
+
+def extreme():
+    """rooms8 and the odd map (a solid brush without sides) with infinite / NaN / huge / denormal coordinates: what the
+    unmodified reference answers when IEEE arithmetic is simply left to run.  NaN payloads in `pos` are the host's."""
+    import oracle
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import extreme_segments
+    from test_hostsim import _odd_map
+    from tools import ibsp, mapgen
+    for name, m, extent in (("extreme_rooms8", mapgen.get_map("rooms8")[0], 2048), ("extreme_odd", _odd_map(), 80)):
+        segs = extreme_segments(24_000, extent, seed=12)
+        path = os.path.join("/tmp", name + ".bsp")
+        ibsp.write(m, path)
+        with np.errstate(all="ignore"):
+            r = oracle.Reference(path).trace(segs)
+        out = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(out, bsp=np.frombuffer(ibsp.to_bytes(m), np.uint8), segs=segs, hit=r["hit"], t=r["t"], pos=r["pos"])
+        print(name, len(segs), "segments,", int(r["hit"].sum()), "hits ->", out, os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":
+    if "--extreme-only" in sys.argv:
+        extreme()
+        sys.exit(0)
     main()

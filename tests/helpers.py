@@ -20,6 +20,15 @@ def load_golden(name):
     return ibsp.from_bytes(z["bsp"].tobytes()), z["segs"], z["hit"], z["t"], z["pos"]
 
 
+def check_against_extreme_golden(hit, t, pos, g_hit, g_t, g_pos, what):
+    """hit and t bit for bit; pos bit for bit where the reference's is finite, NaN where it is NaN (payloads are the host's)"""
+    assert np.array_equal(np.asarray(hit, np.uint8), g_hit), what
+    assert np.array_equal(bits(t), bits(g_t)), what
+    finite = np.isfinite(g_pos).all(axis=1)
+    assert np.array_equal(bits(pos[finite]), bits(g_pos[finite])), what
+    assert np.array_equal(np.asarray(pos), g_pos, equal_nan=True), what
+
+
 def mixed_segments(m, n_uniform=200_000, n_long=200_000, n_short=100_000, n_edge=16384, seed=21):
     from tools import mapgen, seggen
     lo, hi = mapgen.seg_bounds(m)

@@ -270,6 +270,20 @@ def test_golden_reference_outputs(native, name):
     g.close()
 
 
+@pytest.mark.parametrize("name", ["extreme_rooms8", "extreme_odd"])
+def test_golden_reference_outputs_for_extreme_floats(native, name):
+    """the unmodified reference's answers for infinite / NaN / huge / denormal coordinates (and a solid brush without sides)"""
+    from helpers import check_against_extreme_golden, load_golden
+    m, segs, hit, t, pos = load_golden(name)
+    g = native.BspGpu(m)
+    for variant in (1, 3):
+        g.set_option(1, variant)
+        p = np.zeros((len(segs), 4), np.float32)
+        res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=p)
+        check_against_extreme_golden(res["flags"] & 1, res["t"], p[:, :3], hit, t, pos, f"{name} variant {variant}")
+    g.close()
+
+
 @pytest.mark.parametrize("mapname", ["city10k", "tilted"])
 def test_both_schedulers_agree(native, maps, oracle_mod, mapname):
     m, _ = maps(mapname)

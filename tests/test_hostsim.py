@@ -36,6 +36,16 @@ def test_core_matches_golden_reference_outputs(name):
     assert np.array_equal(bits(p[:, :3]), bits(pos))
 
 
+@pytest.mark.parametrize("name", ["extreme_rooms8", "extreme_odd"])
+def test_core_matches_golden_reference_outputs_for_extreme_floats(name):
+    from helpers import check_against_extreme_golden
+    m, segs, hit, t, pos = load_golden(name)
+    sim = HostSim(m)
+    for budgets, kw in ((None, {}), ((0, 0), {}), ((0, 0), {"packed": True, "split_stack": False}), ((0, 0), {"split_stack": True})):
+        res, p = sim.trace(segs, budgets, **kw)
+        check_against_extreme_golden(res["flags"] & 1, res["t"], p[:, :3], hit, t, pos, f"{name} {budgets} {kw}")
+
+
 def _odd_map():
     """hand-laid map with the corner cases of the flattener: a solid brush WITHOUT sides, a leaf
     listing only non-solid brushes, an unreachable node, a leaf listing the same brush twice."""

@@ -57,6 +57,17 @@ def test_port_matches_golden_reference_outputs(oracle_mod, name):
     assert ctr["hits"] == int(hit.sum())
 
 
+@pytest.mark.parametrize("name", ["extreme_rooms8", "extreme_odd"])
+def test_port_matches_golden_reference_outputs_for_extreme_floats(oracle_mod, name):
+    """infinite / NaN / huge / denormal coordinates, and a solid brush without sides: the port answers what the unmodified
+    reference answered (fixtures made by tests/golden/make_golden.py) -- this pins the oracle the GPU is held to there."""
+    from helpers import check_against_extreme_golden
+    m, segs, hit, t, pos = load_golden(name)
+    with np.errstate(all="ignore"):
+        res, ppos, _ = oracle_mod.Port(m).trace(segs)
+    check_against_extreme_golden(res["flags"] & 1, res["t"], ppos, hit, t, pos, name)
+
+
 @pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k", "tilted"])
 def test_port_matches_reference_object(oracle_mod, maps, name):
     if not oracle_mod.have_reference():
