@@ -253,8 +253,8 @@ BSPK_HD bool lane_idle( const Lane & l ) { return l.cur == kCurIdle; }
  * stack_put / stack_get.  A plain array (local memory on the device) is the default; the kernels add a variant
  * that keeps the first slots in shared memory (trace_kernels.cuh: SmemStack). */
 BSPK_HD void stack_put( StackEntry16 * s, int32_t i, int32_t node, float tmin, float tmax ) {
-	StackEntry16 e; e.node = node; e.tmin = tmin; e.tmax = tmax; e.pad = 0;
-	s[ i ] = e;
+	/* three words, not four: local memory interleaves threads word by word, so every word stored is another L1 wavefront */
+	s[ i ].node = node; s[ i ].tmin = tmin; s[ i ].tmax = tmax;
 }
 BSPK_HD void stack_get( const StackEntry16 * s, int32_t i, int32_t & node, float & tmin, float & tmax ) {
 	const StackEntry16 e = s[ i ];
@@ -308,7 +308,7 @@ BSPK_HD int32_t grid_start_ref( const StartGrid & g, float sx, float sy, float s
 	ix = ix < d.dim[ 0 ] ? ix : d.dim[ 0 ] - 1; iy = iy < d.dim[ 1 ] ? iy : d.dim[ 1 ] - 1; iz = iz < d.dim[ 2 ] ? iz : d.dim[ 2 ] - 1;
 	jx = jx < d.dim[ 0 ] ? jx : d.dim[ 0 ] - 1; jy = jy < d.dim[ 1 ] ? jy : d.dim[ 1 ] - 1; jz = jz < d.dim[ 2 ] ? jz : d.dim[ 2 ] - 1;
 	if( ix != jx || iy != jy || iz != jz ) return 0;
-	return g.cells[ ( ( int64_t ) iz * d.dim[ 1 ] + iy ) * d.dim[ 0 ] + ix ];
+	return g.cells[ ( uint32_t ) ( ( iz * d.dim[ 1 ] + iy ) * d.dim[ 0 ] + ix ) ];   /* < 2^26 cells (flatten.cc) */
 }
 
 /* begin the walk at a start reference from grid_start_ref (0 = the root) */
