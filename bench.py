@@ -484,7 +484,9 @@ def map_level_roofline(bpt, traces_per_s, variant):
     try:
         peaks = json.load(open(os.path.join(ROOT, "profiles", "r1_microbench.json")))
         m = bpt["means"]
-        gathers = m["nodes"] + m["sides"] + m["leaf_brushes"]           # node records, side planes, brush references
+        # node records + side-plane PAIRS (two sides per 32-byte gather; a brush's executed sides round up to a pair,
+        # +1/4 gather per brush on average) + brush references
+        gathers = m["nodes"] + m["sides"] / 2.0 + m["solid"] / 4.0 + m["leaf_brushes"]
         in_smem = variant == 1
         peak = peaks["peaks_used_by_bench"]["smem_chase_gathers_per_s" if in_smem else "global_gathers_per_s"]
         return {"level": "shared memory" if in_smem else "L1/L2 read-only path", "record_gathers_per_trace": gathers,
