@@ -76,7 +76,7 @@ static const uint32_t kSectionAlign = 128;
  * walk may start at that reference instead of node 0 and still be bit-identical.  See flatten.cc. */
 struct StartGridDesc {
 	int32_t dim[ 3 ];        /* 0 = no grid */
-	float lo[ 3 ], hi[ 3 ];  /* points must satisfy lo <= p < hi (false for NaN) */
+	float lo[ 3 ], hi[ 3 ];  /* world box; a point is in cell floor((p - lo) * inv) when that lies in [0, dim) (trace_core.h: grid_start_ref) */
 	float inv[ 3 ];          /* cells per unit */
 };
 

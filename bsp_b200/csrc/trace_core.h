@@ -25,6 +25,7 @@
 #ifndef BSPGPU_TRACE_CORE_H
 #define BSPGPU_TRACE_CORE_H
 
+#include <math.h>
 #include <string.h>
 
 #include "map_layout.h"
@@ -297,18 +298,17 @@ struct StartGrid {
 BSPK_HD int32_t grid_start_ref( const StartGrid & g, float sx, float sy, float sz, float ex, float ey, float ez ) {
 	if( !g.cells ) return 0;
 	const StartGridDesc & d = g.d;
-	/* cheap way out for segments longer than a cell (this is only a filter: the decision is the cell test below) */
-	if( !( ( ex - sx ) * d.inv[ 0 ] < 1.0f && ( sx - ex ) * d.inv[ 0 ] < 1.0f && ( ey - sy ) * d.inv[ 1 ] < 1.0f && ( sy - ey ) * d.inv[ 1 ] < 1.0f
-	    && ( ez - sz ) * d.inv[ 2 ] < 1.0f && ( sz - ez ) * d.inv[ 2 ] < 1.0f ) ) return 0;
-	const bool inside = sx >= d.lo[ 0 ] && sx < d.hi[ 0 ] && sy >= d.lo[ 1 ] && sy < d.hi[ 1 ] && sz >= d.lo[ 2 ] && sz < d.hi[ 2 ]
-	                 && ex >= d.lo[ 0 ] && ex < d.hi[ 0 ] && ey >= d.lo[ 1 ] && ey < d.hi[ 1 ] && ez >= d.lo[ 2 ] && ez < d.hi[ 2 ];
-	if( !inside ) return 0;
-	int32_t ix = ( int32_t ) ( ( sx - d.lo[ 0 ] ) * d.inv[ 0 ] ), iy = ( int32_t ) ( ( sy - d.lo[ 1 ] ) * d.inv[ 1 ] ), iz = ( int32_t ) ( ( sz - d.lo[ 2 ] ) * d.inv[ 2 ] );
-	int32_t jx = ( int32_t ) ( ( ex - d.lo[ 0 ] ) * d.inv[ 0 ] ), jy = ( int32_t ) ( ( ey - d.lo[ 1 ] ) * d.inv[ 1 ] ), jz = ( int32_t ) ( ( ez - d.lo[ 2 ] ) * d.inv[ 2 ] );
-	ix = ix < d.dim[ 0 ] ? ix : d.dim[ 0 ] - 1; iy = iy < d.dim[ 1 ] ? iy : d.dim[ 1 ] - 1; iz = iz < d.dim[ 2 ] ? iz : d.dim[ 2 ] - 1;
-	jx = jx < d.dim[ 0 ] ? jx : d.dim[ 0 ] - 1; jy = jy < d.dim[ 1 ] ? jy : d.dim[ 1 ] - 1; jz = jz < d.dim[ 2 ] ? jz : d.dim[ 2 ] - 1;
-	if( ix != jx || iy != jy || iz != jz ) return 0;
-	return g.cells[ ( uint32_t ) ( ( iz * d.dim[ 1 ] + iy ) * d.dim[ 0 ] + ix ) ];   /* < 2^26 cells (flatten.cc) */
+	/* cell coordinates of both endpoints, as floats.  Same cell <=> the floors are equal -- false for NaN, and an
+	 * infinite coordinate fails the range test -- so non-finite input starts at node 0 without a test of its own.
+	 * A point whose coordinate rounds to dim (it lies within an ulp of the upper face) is sent to node 0 as well:
+	 * starting at the root is always exact, only starting below it needs the cell's guarantee. */
+	const float cx = floorf( ( sx - d.lo[ 0 ] ) * d.inv[ 0 ] ), cy = floorf( ( sy - d.lo[ 1 ] ) * d.inv[ 1 ] ), cz = floorf( ( sz - d.lo[ 2 ] ) * d.inv[ 2 ] );
+	const float ox = floorf( ( ex - d.lo[ 0 ] ) * d.inv[ 0 ] ), oy = floorf( ( ey - d.lo[ 1 ] ) * d.inv[ 1 ] ), oz = floorf( ( ez - d.lo[ 2 ] ) * d.inv[ 2 ] );
+	const bool same = cx == ox && cy == oy && cz == oz;
+	const bool inside = cx >= 0.0f && cx < ( float ) d.dim[ 0 ] && cy >= 0.0f && cy < ( float ) d.dim[ 1 ] && cz >= 0.0f && cz < ( float ) d.dim[ 2 ];
+	if( !( same && inside ) ) return 0;
+	const int32_t ix = ( int32_t ) cx, iy = ( int32_t ) cy, iz = ( int32_t ) cz;
+	return g.cells[ ( uint32_t ) ( ( iz * d.dim[ 1 ] + iy ) * d.dim[ 0 ] + ix ) ];   /* < 2^30 cells (flatten.cc) */
 }
 
 /* begin the walk at a start reference from grid_start_ref (0 = the root) */

@@ -420,8 +420,10 @@ __device__ __forceinline__ void lane_load_segment( const TraceParams & p, uint32
 		const float4 b4 = ld_stream4( p.segs + ( size_t ) sidx * 2 + 1 );
 		sx = a.x; sy = a.y; sz = a.z; ex = b4.x; ey = b4.y; ez = b4.z;
 	}
+	/* the start reference first, the lane set-up once after it (one copy of the initialisation instead of one per grid outcome) */
+	const int32_t ref = grid_start_ref( p.grid, sx, sy, sz, ex, ey, ez );   /* 0 when there is no grid */
 	lane_start( l, sx, sy, sz, ex, ey, ez );
-	if( p.grid.cells ) lane_start_at( l, grid_start_ref( p.grid, sx, sy, sz, ex, ey, ez ) );
+	lane_start_at( l, ref );
 }
 
 /* Traversal stack with its first kSlots entries in shared memory.
