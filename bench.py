@@ -284,6 +284,280 @@ def run_reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
+def level_peaks():
+    """measured denominators of the level that holds the map (tools/microbench on one B200, profiles/r2_microbench.json):
+    L2 read bandwidth with L1 bypassed (ld.global.cg over a 96 MB resident set) and the shared-memory bandwidth of the
+    trace's own access pattern (every lane a different dense 16-byte record, one LDS.128)."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_microbench.json")))
+    return {"l2": (max(d[k] for k in d if k.startswith("l2_read_cg_")), "measured: tools/microbench ld.global.cg (L1 bypassed) over L2-resident sets of 16-96 MB, best size (profiles/r2_microbench.json)"),
+            "smem": (d["smem_rec16_gbs"], "measured: tools/microbench scattered dense 16-byte records, one LDS.128 per lane -- the staged kernel's pattern (profiles/r2_microbench.json; conflict-free LDS.128 streams reach %.0f GB/s)" % d["smem_read_gbs"]),
+            "gathers": d}
+
+
+def roofline_block(w, bpt, per_gpu, kernel_ms, variant, workload):
+    """(B - B_io) x traces/s against the measured peak of the level that holds the map (shared memory when
+    the map is staged, else L2), and separately B_io x traces/s against the HBM copy peak."""
+    rate = per_gpu / (kernel_ms * 1e-3)
+    peaks = level_peaks()
+    level = "smem" if variant == 1 else "l2"
+    peak, src = peaks[level]
+    achieved = bpt["b_map"] * rate / 1e9
+    hbm_peak, hbm_src = measured_peak()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp)).get(workload)
+            if tj:
+                traffic = tj["dram_bytes_per_segment"] * per_gpu
+        except Exception:
+            pass
+    m = bpt["means"]
+    gathers = m["nodes"] + m["sides"] / 2.0 + m["solid"] / 4.0 + m["leaf_brushes"]
+    gpeak = peaks["gathers"]["smem_rec16_per_s" if level == "smem" else "gather16_indep_2mb_per_s"]
+    return {"bound": level, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": src, "bytes_per_trace": bpt["b_total"], "bytes_per_trace_map": bpt["b_map"], "bytes_per_trace_io": bpt["b_io"],
+            "visit_means": bpt["means"], "visit_means_source": bpt["source"], "kernel_ms": kernel_ms,
+            "hbm_stream": {"achieved": bpt["b_io"] * rate / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bpt["b_io"] * rate / 1e9 / hbm_peak, "peak_source": hbm_src},
+            "diagnostics": {"record_gathers_per_trace": gathers, "record_gathers_per_s": gathers * rate, "scattered_gather_rate_of_the_level_per_s": gpeak,
+                            "note": "record gathers per second against the microbenchmark's fully scattered rate of the same level; lanes share top-of-tree records, so this is a diagnostic, not a ceiling"},
+            "note": "achieved = algorithmic map bytes (the records the reference walk touches, BASELINE.md section 5) per second; traffic = DRAM bytes per launch from ncu (the 48 B/segment stream and nothing else)"}
+
+
+def check_sample(w, seg_rows, res_rows):
+    """CHECKER (oracle port, allowed here: bench.py's cpu_baseline / parity leg): gathered sample rows against oracle/restate.c"""
+    import oracle
+    exp, _, _ = oracle.Port(w["m"]).trace(np.ascontiguousarray(seg_rows), want_pos=False)
+    bad = int((np.ascontiguousarray(res_rows).view(np.uint32).reshape(-1, 4) != exp.view(np.uint32).reshape(-1, 4)).any(axis=1).sum())
+    return {"checked": int(len(seg_rows)), "mismatches": bad, "against": "oracle/restate.c (bit-exact on all four result words)"}
+
+
+def run_workload(name, a, local, stream, rank, world, per_gpu, steps, want_e2e):
+    """device-resident throughput of one workload on every rank (weak scaling: per_gpu segments per rank per step), hit-count
+    all-reduce and sample gather through the library's NCCL communicator, parity of the gathered sample on rank 0."""
+    import torch
+    import torch.distributed as dist
+    import bsp_b200
+    from bsp_b200 import sharding
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if rank == 0:
+        w = workload_setup(name)                      # rank 0 builds the map cache first, the others then just load it
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        w = workload_setup(name)
+    g = bsp_b200.BspGpu(w["path"], device=local)
+    g.set_stream(stream.cuda_stream)
+    for opt, val in ((2, a.threads), (6, a.refill), (7, a.max_steps), (1, a.variant), (4, a.top_bytes), (3, a.ctas), (8, a.block_segs), (5, a.chunk)):
+        if val is not None:
+            g.set_option(opt, val)
+    libcomm = g if sharding.init_library_comm(g) else None
+
+    first = rank * per_gpu
+    res = {}
+    with torch.cuda.stream(stream):
+        segs = torch.empty((per_gpu, 8), dtype=torch.float32, device="cuda")
+        out = torch.empty((per_gpu, 4), dtype=torch.int32, device="cuda")
+        device_segments(g, w, segs, first, per_gpu)
+        hits_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+        def step():
+            g.trace(segs, out=out, async_=True, stream=False)
+            if libcomm is not None:
+                sharding.reduce_hits(hits_dev, libcomm)       # NCCL inside libbspgpu.so: the hit-count all-reduce (8 bytes)
+            else:
+                g.hit_count_device(hits_dev)
+
+        for _ in range(a.warmup):
+            step()
+        launches_per_step = g.info()["last_launches"]
+
+        sampler = ClockSampler(local) if rank == 0 else None
+        barrier()
+        t_wall0 = time.time()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        ev[0].record(stream)
+        for i in range(steps):
+            kev[i][0].record(stream)
+            g.trace(segs, out=out, async_=True, stream=False)
+            kev[i][1].record(stream)
+            if libcomm is not None:
+                sharding.reduce_hits(hits_dev, libcomm)
+            else:
+                g.hit_count_device(hits_dev)
+            ev[i + 1].record(stream)
+        barrier()
+        t_wall1 = time.time()
+        if sampler:
+            sampler.window(t_wall0, t_wall1)
+        elapsed_ms = ev[0].elapsed_time(ev[-1])
+        kernel_ms = [k0.elapsed_time(k1) for k0, k1 in kev]
+        total_hits = int(hits_dev.item())
+
+        # ---- correctness evidence at THIS world size: every rank's own flag count must add up to the all-reduced counter,
+        #      and a strided sample of every rank's shard (segments + results, gathered over NCCL) is re-traced by the oracle port
+        own = (out[:, 3] & 1).sum().to(torch.int64).reshape(1)
+        if world > 1:
+            dist.all_reduce(own)
+        flag_hits = int(own.item())
+        idx = sharding.sample_indices(per_gpu, a.parity_rows).to("cuda")
+        g_res = sharding.gather_equal(out[idx].contiguous(), libcomm)
+        g_seg = sharding.gather_equal(segs[idx].contiguous(), libcomm)
+        stream.synchronize()
+
+    elapsed_ms = sharding.max_over_ranks(elapsed_ms, "cuda")
+    res["value"] = per_gpu * world * steps / (elapsed_ms * 1e-3)
+    res["ms_per_step"] = elapsed_ms / steps
+    res["hits"] = total_hits
+    if flag_hits != total_hits:
+        raise SystemExit(f"bench.py: {name}: all-reduced hit counter {total_hits} != sum of the ranks' hit flags {flag_hits}")
+    if rank == 0:
+        parity = None
+        if not a.no_cpu or world > 1:
+            parity = check_sample(w, g_seg.reshape(-1, 8).cpu().numpy(), g_res.reshape(-1, 4).cpu().numpy())
+            parity["rows_per_rank"] = int(len(idx)); parity["ranks"] = world
+            parity["gathered_with"] = "ncclSend/ncclRecv inside libbspgpu.so (bspgpu_dist_gather)" if world > 1 else "local"
+            if parity["mismatches"]:
+                raise SystemExit(f"bench.py: {name}: {parity['mismatches']} of {parity['checked']} sampled results differ from the oracle at world size {world}")
+        res["parity_sample"] = parity
+        res["clocks"] = sampler.stop() if sampler else None
+        info = g.info()
+        res["kernel"] = {"variant": info["variant"], "grid": info["grid_ctas"], "block": info["block_threads"], "smem": info["smem_bytes"],
+                         "smem_stack_slots": info["smem_stack_slots"], "general_node_planes": info["num_general_planes"]}
+        res["kernel_ms"] = float(np.mean(kernel_ms))
+        res["launches_per_step"] = launches_per_step
+        res["hit_count_reduction"] = "ncclAllReduce inside libbspgpu.so (bspgpu_dist_hit_count)" if world > 1 else "single GPU"
+    res["w"] = w
+    if want_e2e:
+        res["e2e"] = e2e_leg(g, w, a, local, rank, world, segs, out, barrier)
+    del segs, out
+    g.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+def link_probe(n_bytes=256 << 20, reps=4):
+    """what this box's host link moves with pinned memory: H2D alone, D2H alone, both at once (per direction)"""
+    import torch
+    h_in = torch.empty(n_bytes, dtype=torch.uint8).pin_memory(); h_out = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n_bytes, dtype=torch.uint8, device="cuda"); d_out = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d, d2h):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * n_bytes / (time.perf_counter() - t0) / 1e9
+    run(True, True)
+    return {"h2d_alone_gbs": run(True, False), "d2h_alone_gbs": run(False, True), "both_each_gbs": run(True, True)}
+
+
+def e2e_leg(g, w, a, local, rank, world, segs, out, barrier):
+    """the same metric through the public C-ABI call with HOST buffers: every step copies that step's segments H2D and its
+    results D2H inside the timed region.  Segments are handed over as the reference's own argument layout -- two packed
+    glm::vec3 = 24 bytes (BSP::trace_seg, bsp.h:210; BSP::trace_segs in the C++ mirror).  Measured for both result layouts
+    (16-byte TraceResult, 8-byte bspgpu_result8), with pinned and with pageable caller memory, plus small-batch latencies."""
+    import ctypes as C
+    import torch
+    import bsp_b200
+    from bsp_b200 import sharding
+    e2e_n = min(len(segs), a.e2e_segments)
+    lib = bsp_b200.load_library()
+    bind_to_gpu_numa_node(local)
+    h_in_ptr = lib.bspgpu_host_alloc(e2e_n * 24)
+    h_out_ptr = lib.bspgpu_host_alloc(e2e_n * 16)
+    if not h_in_ptr or not h_out_ptr:
+        raise SystemExit("bench.py: pinned allocation failed")
+    h_in = np.ctypeslib.as_array((C.c_float * (e2e_n * 6)).from_address(h_in_ptr)).reshape(e2e_n, 6)
+    h_out = np.ctypeslib.as_array((C.c_uint32 * (e2e_n * 4)).from_address(h_out_ptr)).reshape(e2e_n, 4)
+    seg_host = segs[:e2e_n].cpu().numpy()
+    h_in[:, 0:3] = seg_host[:, 0:3]
+    h_in[:, 3:6] = seg_host[:, 4:7]
+    del seg_host
+    h_res = h_out.view(bsp_b200.RESULT_DT).reshape(-1)
+    h_res8 = h_out.reshape(-1)[: e2e_n * 2].view(bsp_b200.RESULT8_DT)
+    e2e_steps = max(2, min(a.steps, 5))
+    g.reset_stream()
+    ref_rows = out[:e2e_n: max(1, e2e_n // 65536)].cpu().numpy().view(np.uint32)
+    dev_hits_prefix = int((out[:e2e_n, 3] & 1).sum().item())
+
+    def timed(fn, steps):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()                                                  # H2D + kernels + D2H, synchronous on return
+        torch.cuda.synchronize()
+        return e2e_n * world * steps / sharding.max_over_ranks(time.perf_counter() - t0, "cuda")
+
+    layouts = {}
+    layouts["result16"] = {"value": timed(lambda: g.trace(h_in, out=h_res, packed24=True), e2e_steps), "h2d_bytes_per_step": e2e_n * 24, "d2h_bytes_per_step": e2e_n * 16}
+    if int((h_res["flags"] & 1).sum()) != dev_hits_prefix or not np.array_equal(h_out[:: max(1, e2e_n // 65536)], ref_rows):
+        raise SystemExit("bench.py: host-path results differ from device-path results")
+    layouts["compact8"] = {"value": timed(lambda: g.trace(h_in, out=h_res8, packed24=True, compact=True), e2e_steps), "h2d_bytes_per_step": e2e_n * 24, "d2h_bytes_per_step": e2e_n * 8}
+    stride = max(1, e2e_n // 65536)
+    if int((h_res8["bits"] & 1).sum()) != dev_hits_prefix or not np.array_equal(h_res8["t"][::stride].view(np.uint32), ref_rows[:, 0]) \
+            or not np.array_equal(h_res8["bits"][::stride], ref_rows[:, 3] | ((ref_rows[:, 1] + 1) << 2)):
+        raise SystemExit("bench.py: compact host-path results differ from device-path results")
+    best = max(layouts, key=lambda k: layouts[k]["value"])
+    e2e = {"value": layouts[best]["value"], "unit": "traces/s", "h2d_bytes_per_step": layouts[best]["h2d_bytes_per_step"],
+           "d2h_bytes_per_step": layouts[best]["d2h_bytes_per_step"], "layout": best, "layouts": layouts,
+           "layout_note": "24 B packed vec3 pairs in (the reference's trace_seg arguments); out: result16 = 16-byte TraceResult {t, plane, brush, flags}, "
+                          "compact8 = 8-byte bspgpu_result8 {t, flags | (plane+1) << 2} (BSPGPU_OUT_COMPACT8: everything the reference defines, hit and t, plus the plane extension); "
+                          "pinned host memory, chunked 3-stream pipeline",
+           "segments_per_gpu_per_step": e2e_n, "steps": e2e_steps}
+    if rank == 0:
+        # pageable caller memory (what an existing reference caller has): page-locked for the call vs handed to the driver as it is
+        pg_n = min(e2e_n, 8 * 1024 * 1024)
+        p_in = np.array(h_in[:pg_n]); p_out = np.zeros(pg_n, bsp_b200.RESULT_DT)
+        pageable = {}
+        for opt, key in ((1, "page_locked_for_the_call"), (0, "driver_staged")):
+            g.set_option(17, opt)
+            g.trace(p_in, out=p_out, packed24=True)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                g.trace(p_in, out=p_out, packed24=True)
+            pageable[key] = pg_n * 3 / (time.perf_counter() - t0)
+        g.set_option(17, 1)
+        if not np.array_equal(p_out.view(np.uint32).reshape(-1, 4)[:: max(1, pg_n // 65536)], out[:pg_n: max(1, pg_n // 65536)].cpu().numpy().view(np.uint32)):
+            raise SystemExit("bench.py: pageable host-path results differ from device-path results")
+        e2e["e2e_pageable"] = {"value": pageable["page_locked_for_the_call"], "unit": "traces/s", "segments": pg_n, "variants": pageable,
+                               "note": "plain malloc'ed caller arrays, 24 B in / 16 B out; the library cudaHostRegister()s them for the duration of the call (BSPGPU_OPT_PAGEABLE)"}
+        # small batches: BSP::trace_seg is a batch of one
+        lat = {}
+        for n in (1, 1024, 65536):
+            s_in = np.array(h_in[:n]); s_out = np.zeros(n, bsp_b200.RESULT_DT)
+            for _ in range(20):
+                g.trace(s_in, out=s_out, packed24=True)
+            reps = 200 if n <= 1024 else 50
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                g.trace(s_in, out=s_out, packed24=True)
+            lat[str(n)] = {"us_per_call": 1e6 * (time.perf_counter() - t0) / reps, "grid_ctas": g.info()["grid_ctas"]}
+        e2e["latency"] = lat
+        e2e["link_ceiling"] = link_probe()
+        lc = e2e["link_ceiling"]
+        e2e["link_ceiling"]["segments_per_s_24in_8out"] = min(lc["both_each_gbs"] * 1e9 / 24, lc["both_each_gbs"] * 1e9 / 8)
+        e2e["link_ceiling"]["segments_per_s_24in_16out"] = min(lc["both_each_gbs"] * 1e9 / 24, lc["both_each_gbs"] * 1e9 / 16)
+        e2e["link_ceiling"]["note"] = "pinned copies on this rank's GPU alone (256 MiB x 4); ceiling = the slower direction at the both-ways rate; other ranks idle while rank 0 probes"
+    lib.bspgpu_host_free(h_in_ptr)
+    lib.bspgpu_host_free(h_out_ptr)
+    return e2e
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -299,237 +573,69 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # rank 0 builds the native library and the map cache first, the others then just load them
     if rank == 0:
-        bsp_b200.build()
-        w = workload_setup(a.workload)
+        bsp_b200.build()                                  # the native library, once; the other ranks load it after the barrier
     if world > 1:
         dist.barrier()
-    if rank != 0:
-        w = workload_setup(a.workload)
-
-    g = bsp_b200.BspGpu(w["path"], device=local)
     stream = torch.cuda.Stream()
-    g.set_stream(stream.cuda_stream)
-    for opt, val in ((2, a.threads), (6, a.refill), (7, a.max_steps), (1, a.variant), (4, a.top_bytes), (3, a.ctas), (8, a.block_segs), (5, a.chunk)):
-        if val is not None:
-            g.set_option(opt, val)
 
-    per_gpu = a.segments_per_gpu
-    first = rank * per_gpu
-    with torch.cuda.stream(stream):
-        segs = torch.empty((per_gpu, 8), dtype=torch.float32, device="cuda")
-        out = torch.empty((per_gpu, 4), dtype=torch.int32, device="cuda")
-        device_segments(g, w, segs, first, per_gpu)
-        hits_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
-        sample_idx = torch.arange(0, per_gpu, max(1, per_gpu // 4096), device="cuda")[:4096]
-
-        def step():
-            g.trace(segs, out=out, async_=True)
-            g.hit_count_device(hits_dev)
-            if world > 1:
-                dist.all_reduce(hits_dev)                 # NCCL: the hit-count reduction (8 bytes)
-
-        for _ in range(a.warmup):
-            step()
-        launches_per_step = g.info()["last_launches"]
-
-        sampler = ClockSampler(local) if rank == 0 else None
-        barrier()
-        t_wall0 = time.time()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-        ev[0].record(stream)
-        for i in range(a.steps):
-            kev[i][0].record(stream)
-            g.trace(segs, out=out, async_=True)
-            kev[i][1].record(stream)
-            g.hit_count_device(hits_dev)
-            if world > 1:
-                dist.all_reduce(hits_dev)
-            ev[i + 1].record(stream)
-        barrier()
-        t_wall1 = time.time()
-        if sampler:
-            sampler.window(t_wall0, t_wall1)
-        elapsed_ms = ev[0].elapsed_time(ev[-1])
-        kernel_ms = [k0.elapsed_time(k1) for k0, k1 in kev]
-        total_hits = int(hits_dev.item())
-
-        # small result gather over NCCL (sampled; parity on the gathered rows is checked by rank 0 below)
-        sample_res = out[sample_idx].contiguous()
-        sample_seg = segs[sample_idx].contiguous()
-        if world > 1:
-            gathered = [torch.empty_like(sample_res) for _ in range(world)] if rank == 0 else None
-            dist.gather(sample_res, gathered, dst=0)
-
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    total_segments = per_gpu * world * a.steps
-    value = total_segments / (elapsed_ms * 1e-3)
-
-    # ---------------- e2e: host buffers through the same public call.  Segments are handed over as the
-    # reference's own argument layout -- two packed glm::vec3 = 24 bytes (BSP::trace_seg, bsp.h:210;
-    # BSP::trace_segs in the C++ mirror) -- results come back as 16-byte TraceResults.
-    e2e_n = min(per_gpu, a.e2e_segments)
-    lib = bsp_b200.load_library()
-    bind_to_gpu_numa_node(local)
-    h_in_ptr = lib.bspgpu_host_alloc(e2e_n * 24)
-    h_out_ptr = lib.bspgpu_host_alloc(e2e_n * 16)
-    if not h_in_ptr or not h_out_ptr:
-        raise SystemExit("bench.py: pinned allocation failed")
-    import ctypes as C
-    h_in = np.ctypeslib.as_array((C.c_float * (e2e_n * 6)).from_address(h_in_ptr)).reshape(e2e_n, 6)
-    h_out = np.ctypeslib.as_array((C.c_uint32 * (e2e_n * 4)).from_address(h_out_ptr)).reshape(e2e_n, 4)
-    seg_host = segs[:e2e_n].cpu().numpy()
-    h_in[:, 0:3] = seg_host[:, 0:3]
-    h_in[:, 3:6] = seg_host[:, 4:7]
-    del seg_host
-    h_res = h_out.view(bsp_b200.RESULT_DT).reshape(-1)
-    e2e_steps = max(2, min(a.steps, 5))
-    g.reset_stream()
-    for _ in range(2):
-        g.trace(h_in, out=h_res, packed24=True)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        g.trace(h_in, out=h_res, packed24=True)            # H2D + kernels + D2H, synchronous on return
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_n * world * e2e_steps / float(te.item())
-    e2e_hits = int((h_res["flags"] & 1).sum())
-    dev_hits_prefix = int((out[:e2e_n, 3] & 1).sum().item())
-    if e2e_hits != dev_hits_prefix:
-        raise SystemExit(f"bench.py: host-path results differ from device-path results ({e2e_hits} vs {dev_hits_prefix} hits)")
-    if not np.array_equal(h_out[:: max(1, e2e_n // 65536)], out[:e2e_n: max(1, e2e_n // 65536)].cpu().numpy().view(np.uint32)):
-        raise SystemExit("bench.py: host-path results differ from device-path results")
-
+    main_res = run_workload(a.workload, a, local, stream, rank, world, a.segments_per_gpu, a.steps, want_e2e=True)
+    w = main_res.pop("w")
+    line = None
     if rank == 0:
-        clocks = sampler.stop() if sampler else None
-        cpu_line, counters, parity = None, None, None
+        cpu_line, counters = None, None
         if world == 1 and not a.no_cpu:
-            extras, cpu_line = cpu_reference(w, parity=(sample_seg.cpu().numpy(), sample_res.cpu().numpy()))
-            counters, parity = extras.get("counters"), extras.get("parity")
+            extras, cpu_line = cpu_reference(w)
+            counters = extras.get("counters")
         bpt = algorithmic_bytes(w, counters)
-        peak, peak_src = measured_peak()
-        mean_kernel_ms = float(np.mean(kernel_ms))
-        achieved = bpt["b_total"] * per_gpu / (mean_kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp)).get(a.workload)
-                if tj:
-                    traffic = tj["dram_bytes_per_segment"] * per_gpu
-            except Exception:
-                pass
-        info = g.info()
+        per_gpu = a.segments_per_gpu
         line = {
-            "metric": "bsp_segment_traces_per_sec", "value": value, "unit": "traces/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "bsp_segment_traces_per_sec", "value": main_res["value"], "unit": "traces/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": a.workload, "map": w["map"], "map_counts": w["m"].counts(), "segments_per_gpu_per_step": per_gpu,
                        "segment_kind": w["kind"], "seed": w["seed"], "parallelism": f"segments sharded x{world}, map replicated",
                        "l2": f"inputs larger than L2 ({per_gpu * 48 / 1e9:.1f} GB streamed per step per GPU)",
-                       "kernel": {"variant": info["variant"], "grid": info["grid_ctas"], "block": info["block_threads"], "smem": info["smem_bytes"]}},
-            "hits": total_hits, "parity_sample": parity,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "bytes_per_trace": bpt["b_total"], "bytes_per_trace_map": bpt["b_map"],
-                         "bytes_per_trace_io": bpt["b_io"], "visit_means": bpt["means"], "visit_means_source": bpt["source"], "kernel_ms": mean_kernel_ms,
-                         "hbm_stream_gbs": bpt["b_io"] * per_gpu / (mean_kernel_ms * 1e-3) / 1e9,
-                         "map_level": map_level_roofline(bpt, per_gpu / (mean_kernel_ms * 1e-3), info["variant"]),
-                         "note": "achieved = algorithmic bytes (map records the reference walk touches + 48 B segment/result I/O) per second; "
-                                 "map bytes are served from shared memory / L1 / L2, only the I/O stream reaches HBM"},
-            "e2e": {"value": e2e_value, "unit": "traces/s", "h2d_bytes_per_step": e2e_n * 24, "d2h_bytes_per_step": e2e_n * 16,
-                    "layout": "24 B packed vec3 pairs in (the reference's trace_seg arguments), 16 B TraceResult out, pinned host memory, chunked 3-stream pipeline",
-                    "segments_per_gpu_per_step": e2e_n, "steps": e2e_steps},
-            "gpu_launches": launches_per_step * a.steps,
-            "clocks": clocks,
+                       "kernel": main_res["kernel"], "collectives": main_res["hit_count_reduction"]},
+            "hits": main_res["hits"], "parity_sample": main_res["parity_sample"],
+            "roofline": roofline_block(w, bpt, per_gpu, main_res["kernel_ms"], main_res["kernel"]["variant"], a.workload),
+            "e2e": main_res["e2e"],
+            "gpu_launches": main_res["launches_per_step"] * a.steps,
+            "clocks": main_res["clocks"],
+            "provenance": "every number in this line was measured by this run (driver-run when the driver launched it)",
         }
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
-        if world == 1 and a.also and a.also != a.workload:
-            # the other single-GPU configuration of BASELINE.json (configs[1]: rooms8, 64 Mi uniform segments, map staged
-            # in shared memory), device-resident, same timing rules -- reported beside the headline, not instead of it
-            try:
-                del segs, out
-                torch.cuda.empty_cache()
-                line["also"] = {a.also: secondary_workload(a.also, a, local, stream)}
-            except Exception as e:  # pragma: no cover
-                line["also"] = {a.also: {"error": str(e)}}
-        print(json.dumps(line), flush=True)
 
-    lib.bspgpu_host_free(h_in_ptr)
-    lib.bspgpu_host_free(h_out_ptr)
-    g.close()
+    # ---- the other configurations of BASELINE.json, device-resident, same timing rules, each with its own parity sample:
+    #      C2 rooms8 (64 Mi uniform segments, map staged in shared memory), C4 camera grids on the city, C5 mega200k short moves.
+    #      At N > 1 only C5 is repeated (BASELINE.json quotes it on 8 GPUs); the others are single-GPU configurations.
+    also = [x for x in a.also.split(",") if x and x != a.workload]
+    if world > 1:
+        also = [x for x in also if x == "mega200k-short"]
+    also_out = {}
+    for name in also:
+        try:
+            n2 = 64 * 1024 * 1024 if name == "rooms8-uniform" else a.segments_per_gpu
+            r2 = run_workload(name, a, local, stream, rank, world, n2, max(3, min(a.steps, 10)), want_e2e=False)
+            w2 = r2.pop("w")
+            if rank == 0:
+                bpt2 = algorithmic_bytes(w2)              # committed visit counts (profiles/bytes_per_trace.json)
+                also_out[name] = {"value": r2["value"], "unit": "traces/s", "n_gpus": world, "ms_per_step": r2["ms_per_step"], "segments_per_gpu_per_step": n2,
+                                  "hits": r2["hits"], "parity_sample": r2["parity_sample"], "kernel": r2["kernel"], "clocks": r2["clocks"],
+                                  "roofline": roofline_block(w2, bpt2, n2, r2["kernel_ms"], r2["kernel"]["variant"], name)}
+        except SystemExit:
+            raise
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                also_out[name] = {"error": repr(e)}
+    if rank == 0:
+        if also_out:
+            line["also"] = also_out
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def map_level_roofline(bpt, traces_per_s, variant):
-    """the level that actually holds the map: record gathers per second against the measured scattered-gather
-    rate of that level (profiles/r1_microbench.json, tools/microbench) -- the binding resource of this kernel."""
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "profiles", "r1_microbench.json")))
-        m = bpt["means"]
-        # node records + side-plane PAIRS (two sides per 32-byte gather; a brush's executed sides round up to a pair,
-        # +1/4 gather per brush on average) + brush references
-        gathers = m["nodes"] + m["sides"] / 2.0 + m["solid"] / 4.0 + m["leaf_brushes"]
-        in_smem = variant == 1
-        peak = peaks["peaks_used_by_bench"]["smem_chase_gathers_per_s" if in_smem else "global_gathers_per_s"]
-        return {"level": "shared memory" if in_smem else "L1/L2 read-only path", "record_gathers_per_trace": gathers,
-                "achieved_gathers_per_s": gathers * traces_per_s, "peak_gathers_per_s": peak, "frac": gathers * traces_per_s / peak,
-                "map_bytes_gbs": bpt["b_map"] * traces_per_s / 1e9,
-                "level_bandwidth_gbs": peaks["smem_read_gbs" if in_smem else "l2_read_gbs"],
-                "note": "peak = fully scattered 32-byte gathers (every lane a different record); the trace's top-of-tree gathers are "
-                        "shared between lanes, so frac can exceed 1"}
-    except Exception as e:  # pragma: no cover
-        return {"error": str(e)}
-
-
-def secondary_workload(name, a, local, stream):
-    import torch
-    import bsp_b200
-    w2 = workload_setup(name)
-    n2 = 64 * 1024 * 1024
-    g2 = bsp_b200.BspGpu(w2["path"], device=local)
-    g2.set_stream(stream.cuda_stream)
-    with torch.cuda.stream(stream):
-        segs2 = torch.empty((n2, 8), dtype=torch.float32, device="cuda")
-        out2 = torch.empty((n2, 4), dtype=torch.int32, device="cuda")
-        device_segments(g2, w2, segs2, 0, n2)
-        for _ in range(3):
-            g2.trace(segs2, out=out2, async_=True)
-        torch.cuda.synchronize()
-        steps = max(3, min(a.steps, 10))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            g2.trace(segs2, out=out2, async_=True)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-    bpt = algorithmic_bytes(w2)          # committed visit counts
-    peak, _ = measured_peak()
-    info = g2.info()
-    res = {"value": n2 / (ms * 1e-3), "unit": "traces/s", "ms_per_step": ms, "steps": steps, "segments_per_step": n2,
-           "hits": g2.hit_count(), "bytes_per_trace": bpt["b_total"],
-           "roofline_frac": bpt["b_total"] * n2 / (ms * 1e-3) / 1e9 / peak,
-           "kernel": {"variant": info["variant"], "grid": info["grid_ctas"], "block": info["block_threads"], "smem": info["smem_bytes"]}}
-    g2.close()
-    return res
 
 
 def main():
@@ -542,7 +648,9 @@ def main():
     ap.add_argument("--segments-per-gpu", type=int, default=128 * 1024 * 1024)
     ap.add_argument("--e2e-segments", type=int, default=32 * 1024 * 1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--also", default="rooms8-uniform", help="second workload reported under 'also' at N=1 ('' to skip)")
+    ap.add_argument("--also", default="rooms8-uniform,city10k-camera,mega200k-short",
+                    help="other BASELINE.json configurations reported under 'also' (comma list, '' to skip); at N>1 only mega200k-short runs")
+    ap.add_argument("--parity-rows", type=int, default=4096, help="rows of every rank's shard re-traced by the oracle port")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--threads", type=int, default=None)
     ap.add_argument("--refill", type=int, default=None)

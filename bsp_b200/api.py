@@ -12,15 +12,18 @@ RESULT_DT = np.dtype([("t", "<f4"), ("plane", "<i4"), ("brush", "<i4"), ("flags"
 SEGMENT_FLOATS = 8
 HIT, STARTSOLID = 1, 2
 
-SEGS_DEVICE, OUT_DEVICE, SEGS_PACKED24, ASYNC = 1, 2, 4, 8
+RESULT8_DT = np.dtype([("t", "<f4"), ("bits", "<u4")])      # bspgpu_result8: bits = flags | (plane + 1) << 2
+SEGS_DEVICE, OUT_DEVICE, SEGS_PACKED24, ASYNC, OUT_COMPACT8 = 1, 2, 4, 8, 16
 VARIANT_AUTO, VARIANT_SMEM, VARIANT_TOPTREE, VARIANT_GLOBAL = 0, 1, 2, 3
 OPT_VARIANT, OPT_BLOCK_THREADS, OPT_CTAS_PER_SM, OPT_TOPTREE_BYTES, OPT_CHUNK_SEGMENTS, OPT_REFILL, \
-    OPT_MAX_STEPS, OPT_BLOCK_SEGS, OPT_SCHEDULER, OPT_SIDE_STEPS, OPT_LEAF_THRESHOLD, OPT_MAX_LAUNCH_SEGMENTS, OPT_START_GRID, OPT_PACKED_NODES, OPT_SMEM_STACK = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
+    OPT_MAX_STEPS, OPT_BLOCK_SEGS, OPT_SCHEDULER, OPT_SIDE_STEPS, OPT_LEAF_THRESHOLD, OPT_MAX_LAUNCH_SEGMENTS, OPT_START_GRID = range(1, 14)
+OPT_SMEM_STACK, OPT_BIN_SEGMENTS, OPT_PAGEABLE = 15, 16, 17
 
 # every symbol include/bspgpu.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = (
-    "bspgpu_create", "bspgpu_create_from_file", "bspgpu_destroy", "bspgpu_trace", "bspgpu_trace_pos",
-    "bspgpu_hit_count", "bspgpu_hit_count_device", "bspgpu_leaf", "bspgpu_generate", "bspgpu_set_option", "bspgpu_set_stream",
+    "bspgpu_create", "bspgpu_create_opts", "bspgpu_create_from_file", "bspgpu_destroy", "bspgpu_trace", "bspgpu_trace_pos", "bspgpu_trace_stream",
+    "bspgpu_hit_count", "bspgpu_hit_count_device", "bspgpu_leaf", "bspgpu_leaf_clusters", "bspgpu_set_vis", "bspgpu_visible_leaves",
+    "bspgpu_generate", "bspgpu_set_option", "bspgpu_set_stream",
     "bspgpu_reset_stream", "bspgpu_get_info", "bspgpu_sync", "bspgpu_host_alloc", "bspgpu_host_free", "bspgpu_shard_range",
     "bspgpu_last_error", "bspgpu_abi_version",
 )
@@ -47,7 +50,13 @@ class Info(C.Structure):
                 ("block_threads", C.c_uint32), ("grid_ctas", C.c_uint32), ("smem_bytes", C.c_uint32),
                 ("tree_depth", C.c_uint32), ("num_nodes", C.c_uint32), ("num_brush_refs", C.c_uint32),
                 ("num_sides", C.c_uint32), ("map_bytes", C.c_uint64), ("last_kernel_ms", C.c_float),
-                ("last_launches", C.c_uint32), ("start_grid_cells", C.c_uint32), ("staged_bytes", C.c_uint32)]
+                ("last_launches", C.c_uint32), ("start_grid_cells", C.c_uint32), ("staged_bytes", C.c_uint32),
+                ("num_general_planes", C.c_uint32), ("num_leaves", C.c_uint32), ("num_clusters", C.c_uint32),
+                ("smem_stack_slots", C.c_uint32), ("last_prepass_ms", C.c_float)]
+
+
+class CreateOptions(C.Structure):
+    _fields_ = [("start_grid_cells", C.c_int64), ("general_planes_only", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -69,13 +78,18 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(path)
     vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
     lib.bspgpu_create.argtypes = [C.POINTER(vp), C.POINTER(MapDesc), i32]
+    lib.bspgpu_create_opts.argtypes = [C.POINTER(vp), C.POINTER(MapDesc), i32, C.POINTER(CreateOptions)]
     lib.bspgpu_create_from_file.argtypes = [C.POINTER(vp), C.c_char_p, i32]
     lib.bspgpu_destroy.argtypes = [vp]; lib.bspgpu_destroy.restype = None
     lib.bspgpu_trace.argtypes = [vp, vp, u64, vp, u32]
     lib.bspgpu_trace_pos.argtypes = [vp, vp, u64, vp, vp, u32]
+    lib.bspgpu_trace_stream.argtypes = [vp, vp, u64, vp, vp, u32, vp]
     lib.bspgpu_hit_count.argtypes = [vp, C.POINTER(u64)]
     lib.bspgpu_hit_count_device.argtypes = [vp, vp]
     lib.bspgpu_leaf.argtypes = [vp, vp, u32, u64, vp, u32]
+    lib.bspgpu_leaf_clusters.argtypes = [vp, vp, u32, u64, vp, vp, C.c_int32, vp, u32]
+    lib.bspgpu_set_vis.argtypes = [vp, vp, u64]
+    lib.bspgpu_visible_leaves.argtypes = [vp, vp, vp, C.POINTER(C.c_int32)]
     lib.bspgpu_generate.argtypes = [vp, C.POINTER(GenDesc), u64, u64, vp]
     lib.bspgpu_set_option.argtypes = [vp, i32, C.c_int64]
     lib.bspgpu_set_stream.argtypes = [vp, vp]
@@ -122,12 +136,15 @@ def _is_device(x) -> bool:
 class BspGpu:
     """One ``bspgpu_t`` handle: a map flattened into HBM on one device."""
 
-    def __init__(self, source, device: int = -1):
-        """``source``: path to an IBSP file, or an object with the seven lump arrays
-        (``tools.ibsp.IBSP``)."""
+    def __init__(self, source, device: int = -1, start_grid_cells: int = 0, general_planes_only: bool = False):
+        """``source``: path to an IBSP file, or an object with the seven lump arrays (``tools.ibsp.IBSP``; its ``vis``
+        lump, when present, is uploaded too).  ``start_grid_cells`` / ``general_planes_only``: bspgpu_create_options
+        (lump objects only)."""
         self.lib = load_library()
         self.h = C.c_void_p()
         if isinstance(source, (str, bytes, os.PathLike)):
+            if start_grid_cells or general_planes_only:
+                raise ValueError("create options need a lump object, not a file path")
             rc = self.lib.bspgpu_create_from_file(C.byref(self.h), os.fsencode(source), device)
         else:
             desc = MapDesc()
@@ -137,7 +154,13 @@ class BspGpu:
                 keep.append(arr)
                 setattr(desc, nm, arr.ctypes.data if arr.size else None)
                 setattr(desc, "num_" + nm, len(arr))
-            rc = self.lib.bspgpu_create(C.byref(self.h), C.byref(desc), device)
+            opts = CreateOptions(int(start_grid_cells), 1 if general_planes_only else 0, 0)
+            rc = self.lib.bspgpu_create_opts(C.byref(self.h), C.byref(desc), device, C.byref(opts))
+            if rc == 0:
+                vis = getattr(source, "vis", None)
+                if vis is not None and len(vis) >= 8:
+                    vis = np.ascontiguousarray(vis, np.uint8)
+                    self._check(self.lib.bspgpu_set_vis(self.h, vis.ctypes.data, len(vis)))
         self._check(rc)
 
     def _check(self, rc: int):
@@ -183,25 +206,48 @@ class BspGpu:
         self._check(self.lib.bspgpu_hit_count_device(self.h, _ptr(dev_i64)))
 
     # -- the hot path
-    def trace(self, segs, out=None, pos=None, n=None, packed24=False, async_=False):
+    def trace(self, segs, out=None, pos=None, n=None, packed24=False, async_=False, compact=False, stream=None):
         """segs: (n,8) float32 numpy array / torch tensor (host or cuda), or (n,6) with packed24.
-        out: RESULT_DT array or (n,4) int32/float32 tensor; allocated (numpy) when segs is a numpy array."""
+        out: RESULT_DT array or (n,4) int32/float32 tensor (compact: RESULT8_DT / (n,2)); allocated (numpy) when segs is a
+        numpy array and neither out nor pos is given.  Returns out (or pos when only pos was asked for).
+        CUDA tensors: the call is enqueued on `stream` (a raw cudaStream_t) -- by default torch's CURRENT stream, so it is
+        ordered after the kernels that produced `segs`; pass stream=False to use whatever bspgpu_set_stream installed."""
+        floats = 6 if packed24 else SEGMENT_FLOATS
+        if not hasattr(segs, "shape") or len(segs.shape) != 2 or int(segs.shape[1]) != floats:
+            raise ValueError(f"segs must be (n, {floats}) float32" + (" (packed24)" if packed24 else ""))
+        if str(segs.dtype).replace("torch.", "") != "float32":
+            raise ValueError(f"segs must be float32, not {segs.dtype}")
         if n is None:
             n = int(segs.shape[0])
+        if n > int(segs.shape[0]):
+            raise ValueError("n exceeds the number of segments passed")
         if out is None and pos is None:
             if not isinstance(segs, np.ndarray):
                 raise ValueError("pass `out` for tensor inputs")
-            out = np.zeros(n, RESULT_DT)
-        flags = (SEGS_DEVICE if _is_device(segs) else 0) | (SEGS_PACKED24 if packed24 else 0) | (ASYNC if async_ else 0)
+            out = np.zeros(n, RESULT8_DT if compact else RESULT_DT)
+        for name, x, need in (("out", out, n * (8 if compact else 16)), ("pos", pos, n * 16)):
+            if x is not None:
+                have = x.nbytes if isinstance(x, np.ndarray) else x.numel() * x.element_size()
+                if have < need:
+                    raise ValueError(f"{name} holds {have} bytes, {need} needed for {n} segments")
+        flags = (SEGS_DEVICE if _is_device(segs) else 0) | (SEGS_PACKED24 if packed24 else 0) | (ASYNC if async_ else 0) | (OUT_COMPACT8 if compact else 0)
         outs_dev = [_is_device(x) for x in (out, pos) if x is not None]
         if any(outs_dev) and not all(outs_dev):
             raise ValueError("out and pos must both be host or both be device")
         if outs_dev and outs_dev[0]:
             flags |= OUT_DEVICE
-        self._check(self.lib.bspgpu_trace_pos(self.h, _ptr(segs), n, _ptr(out), _ptr(pos), flags))
-        return out
+        if stream is None and (flags & (SEGS_DEVICE | OUT_DEVICE)):
+            import torch
+            stream = torch.cuda.current_stream(segs.device if _is_device(segs) else out.device if out is not None else pos.device).cuda_stream
+        if stream is None or stream is False:
+            self._check(self.lib.bspgpu_trace_pos(self.h, _ptr(segs), n, _ptr(out), _ptr(pos), flags))
+        else:
+            self._check(self.lib.bspgpu_trace_stream(self.h, _ptr(segs), n, _ptr(out), _ptr(pos), flags, stream))
+        return out if out is not None else pos
 
     def leaf(self, pts, out=None):
+        if len(pts.shape) != 2 or int(pts.shape[1]) < 3 or str(pts.dtype).replace("torch.", "") != "float32":
+            raise ValueError("pts must be (n, >=3) float32")
         n = int(pts.shape[0])
         stride = int(pts.shape[1])
         if out is None:
@@ -209,6 +255,24 @@ class BspGpu:
         flags = (SEGS_DEVICE if _is_device(pts) else 0) | (OUT_DEVICE if _is_device(out) else 0)
         self._check(self.lib.bspgpu_leaf(self.h, _ptr(pts), stride, n, _ptr(out), flags))
         return out
+
+    def leaf_clusters(self, pts, from_cluster: int = -1, want_visible: bool = False):
+        """host points -> (leaf, cluster[, visible from `from_cluster`]) per point (bspgpu_leaf_clusters)"""
+        pts = np.ascontiguousarray(pts, np.float32)
+        n = len(pts)
+        leaf, cluster = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        vis = np.zeros(n, np.uint8) if want_visible else None
+        self._check(self.lib.bspgpu_leaf_clusters(self.h, pts.ctypes.data, pts.shape[1], n, leaf.ctypes.data, cluster.ctypes.data,
+                                                  from_cluster, vis.ctypes.data if want_visible else None, 0))
+        return (leaf, cluster, vis) if want_visible else (leaf, cluster)
+
+    def visible_leaves(self, pos):
+        """the loop of bspr_render (bsp_renderer.cc:147-168): (visible flag per leaf, viewer cluster)"""
+        p = np.ascontiguousarray(pos, np.float32)
+        vis = np.zeros(self.info()["num_leaves"], np.uint8)
+        c = C.c_int32()
+        self._check(self.lib.bspgpu_visible_leaves(self.h, p.ctypes.data, vis.ctypes.data, C.byref(c)))
+        return vis, c.value
 
     def generate(self, dev_segs, first: int, count: int, kind: int, seed: int, lo, hi, len_lo=0.0, len_hi=0.0,
                  views=None, width=0, height=0, tan_half=1.0, far=32768.0):

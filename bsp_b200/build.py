@@ -47,11 +47,13 @@ def _sources(*dirs_) -> list[str]:
     return out
 
 
-def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> None:
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, experiments: bool = False) -> None:
+    """experiments=True adds -DBSPGPU_EXPERIMENTS: the measured-slower round-1 alternatives (one thread per segment, top of the
+    tree in shared memory) become selectable again; the product build leaves them out."""
     deps = _sources(CSRC, os.path.join(os.path.dirname(HERE), "include"))
     if force or _stale(LIB_GPU, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + [
-            "-o", LIB_GPU, os.path.join(CSRC, "bspgpu.cu"), os.path.join(CSRC, "flatten.cc")]
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + (["-DBSPGPU_EXPERIMENTS"] if experiments else []) + [
+            "-o", LIB_GPU, os.path.join(CSRC, "bspgpu.cu"), os.path.join(CSRC, "bspgpu_multi.cu"), os.path.join(CSRC, "flatten.cc"), "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or ptxas_info or r.returncode:
             print(" ".join(cmd)); print(r.stdout); print(r.stderr)
@@ -84,4 +86,4 @@ def build_microbench(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     import sys
-    build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv)
+    build(force="--force" in sys.argv or "--experiments" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv, experiments="--experiments" in sys.argv)

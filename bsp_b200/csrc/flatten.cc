@@ -49,7 +49,7 @@ std::string fmt( const char * f, long long a = 0, long long b = 0, long long c =
 
 } // namespace
 
-int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
+int flatten_map( const bspgpu_map_desc & L, const FlattenOptions & opt, FlatMap & out, std::string & err ) {
 	if( L.num_nodes == 0 || !L.nodes ) { err = "map has no nodes (the trace starts at node 0, bsp.cc:263)"; return BSPGPU_E_MAP; }
 	if( ( L.num_planes && !L.planes ) || ( L.num_leaves && !L.leaves ) || ( L.num_brushes && !L.brushes ) ||
 	    ( L.num_brush_sides && !L.brush_sides ) || ( L.num_leaf_brushes && !L.leaf_brushes ) || ( L.num_textures && !L.textures ) ) {
@@ -136,18 +136,40 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 		if( osides.size() >= 0x7ffffff0u ) { err = "too many brush sides"; return BSPGPU_E_MAP; }
 	}
 
-	/* ---- emit */
+	/* ---- emit.  A node whose plane normal is bitwise +e_x / +e_y / +e_z keeps only the axis (map_layout.h: NodeRec);
+	 *      every other plane goes to the general-plane section. */
+	auto axis_of = [&]( const DiskPlane & pl ) -> int {
+		uint32_t b[ 3 ];
+		memcpy( b, pl.n, 12 );
+		const uint32_t one = 0x3f800000u;
+		if( b[ 0 ] == one && b[ 1 ] == 0 && b[ 2 ] == 0 ) return 0;
+		if( b[ 0 ] == 0 && b[ 1 ] == one && b[ 2 ] == 0 ) return 1;
+		if( b[ 0 ] == 0 && b[ 1 ] == 0 && b[ 2 ] == one ) return 2;
+		return -1;
+	};
 	const uint32_t num_nodes = ( uint32_t ) order.size();
 	std::vector< NodeRec > onodes( num_nodes );
+	std::vector< NodeOrig > oorig( num_nodes );
+	std::vector< PlaneRec > ogplanes;
+	std::vector< PlaneRec > full_planes( num_nodes );   /* every node's plane, for the start grid below */
 	std::vector< BrushRef > orefs;
 	for( uint32_t i = 0; i < num_nodes; i++ ) {
 		const DiskNode & nd = nodes[ order[ i ] ];
 		const DiskPlane & pl = planes[ nd.plane ];
 		NodeRec & o = onodes[ i ];
-		o.nx = pl.n[ 0 ]; o.ny = pl.n[ 1 ]; o.nz = pl.n[ 2 ]; o.d = pl.d;
+		PlaneRec full; full.nx = pl.n[ 0 ]; full.ny = pl.n[ 1 ]; full.nz = pl.n[ 2 ]; full.d = pl.d;
+		full_planes[ i ] = full;
+		o.d = pl.d;
+		const int ax = opt.general_planes_only ? -1 : axis_of( pl );
+		if( ax >= 0 ) o.w = ( uint32_t ) ax;
+		else {
+			if( ogplanes.size() >= 0xfffffff0u - kGeneralPlane ) { err = "too many general node planes"; return BSPGPU_E_MAP; }
+			o.w = kGeneralPlane + ( uint32_t ) ogplanes.size();
+			ogplanes.push_back( full );
+		}
 		for( int k = 0; k < 2; k++ ) {
 			const int32_t c = nd.children[ k ];
-			o.orig_child[ k ] = c;
+			oorig[ i ].orig_child[ k ] = c;
 			if( c >= 0 ) { o.child[ k ] = bfs_of[ c ]; continue; }
 			const DiskLeaf & lf = leaves[ -( ( int64_t ) c + 1 ) ];
 			const size_t first_ref = orefs.size();
@@ -167,62 +189,21 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	}
 
 	MapImageLayout & lay = out.layout;
-	const uint32_t num_sides_out = ( uint32_t ) osides.size();
-	lay.num_nodes = num_nodes; lay.num_refs = ( uint32_t ) orefs.size(); lay.num_sides = num_sides_out;
-	lay.tree_depth = tree_depth;
+	const uint32_t num_sides_out = ( uint32_t ) osides.size();   /* even */
+	const uint64_t half_bytes = ( uint64_t ) ( num_sides_out / 2 ) * sizeof( SideRec );
+	lay.num_nodes = num_nodes; lay.num_gplanes = ( uint32_t ) ogplanes.size(); lay.num_refs = ( uint32_t ) orefs.size(); lay.num_sides = num_sides_out;
+	lay.tree_depth = tree_depth; lay.num_leaves = L.num_leaves;
 	lay.off_nodes = 0;
-	lay.off_refs = align_up( lay.off_nodes + ( uint64_t ) num_nodes * sizeof( NodeRec ), kSectionAlign );
-	lay.off_sides = align_up( lay.off_refs + ( uint64_t ) orefs.size() * sizeof( BrushRef ), kSectionAlign );
-	lay.staged_bytes = align_up( lay.off_sides + ( uint64_t ) num_sides_out * sizeof( SideRec ), kSectionAlign );
-	lay.off_side_plane = lay.staged_bytes;
-	lay.off_qnodes = align_up( lay.off_side_plane + ( uint64_t ) num_sides_out * sizeof( uint32_t ), kSectionAlign );
-	lay.off_grid = align_up( lay.off_qnodes + ( uint64_t ) num_nodes * sizeof( QNodeRec ), kSectionAlign );
-
-	/* ---- two-level records for the read-only-path walk (map_layout.h: QNodeRec) */
-	std::vector< QNodeRec > qnodes( num_nodes );
-	{
-		auto axis_of = [&]( const NodeRec & n ) -> int {   /* 0/1/2 for a bitwise +unit normal, else -1 */
-			uint32_t b[ 3 ];
-			memcpy( b, &n.nx, 12 );
-			const uint32_t one = 0x3f800000u;
-			if( b[ 0 ] == one && b[ 1 ] == 0 && b[ 2 ] == 0 ) return 0;
-			if( b[ 0 ] == 0 && b[ 1 ] == one && b[ 2 ] == 0 ) return 1;
-			if( b[ 0 ] == 0 && b[ 1 ] == 0 && b[ 2 ] == one ) return 2;
-			return -1;
-		};
-		auto bits = []( float f ) { uint32_t u; memcpy( &u, &f, 4 ); return u; };
-		const bool disable = getenv( "BSPGPU_NO_PACKED_NODES" ) != nullptr;   /* test knob: general records only */
-		for( uint32_t i = 0; i < num_nodes; i++ ) {
-			const NodeRec & n = onodes[ i ];
-			QNodeRec & q = qnodes[ i ];
-			const int ax = disable ? -1 : axis_of( n );
-			if( ax < 0 ) {
-				q.w[ 0 ] = bits( n.nx ); q.w[ 1 ] = bits( n.ny ); q.w[ 2 ] = bits( n.nz ); q.w[ 3 ] = bits( n.d );
-				q.w[ 4 ] = ( uint32_t ) n.child[ 0 ]; q.w[ 5 ] = ( uint32_t ) n.child[ 1 ]; q.w[ 6 ] = 0; q.w[ 7 ] = 0;
-				continue;
-			}
-			uint32_t w = kQPacked | ( ( uint32_t ) ax << kQAxisShift );
-			uint32_t base = 0;
-			bool have_base = false;
-			q.w[ 0 ] = bits( n.d ); q.w[ 1 ] = 0; q.w[ 2 ] = 0;
-			for( int k = 0; k < 2; k++ ) {
-				const int32_t c = n.child[ k ];
-				uint32_t g_a = ( uint32_t ) c, g_b = 0;          /* not expanded: the child's own reference */
-				const int cax = c >= 0 ? axis_of( onodes[ c ] ) : -1;
-				const bool fits = c >= 0 && ( uint32_t ) c < ( 1u << ( 32 - kQBaseShift ) );
-				const bool consecutive = !have_base || ( uint32_t ) c == base + 1;   /* breadth-first numbering; checked, not assumed */
-				if( cax >= 0 && fits && consecutive ) {
-					w |= k == 0 ? kQExpand0 : kQExpand1;
-					w |= ( uint32_t ) cax << ( k == 0 ? kQAxis0Shift : kQAxis1Shift );
-					q.w[ 1 + k ] = bits( onodes[ c ].d );
-					g_a = ( uint32_t ) onodes[ c ].child[ 0 ]; g_b = ( uint32_t ) onodes[ c ].child[ 1 ];
-					if( !have_base ) { base = ( uint32_t ) c; have_base = true; }
-				}
-				q.w[ 3 + 2 * k ] = g_a; q.w[ 4 + 2 * k ] = g_b;
-			}
-			q.w[ 7 ] = w | ( base << kQBaseShift );
-		}
-	}
+	lay.off_gplanes = align_up( lay.off_nodes + ( uint64_t ) num_nodes * sizeof( NodeRec ), kSectionAlign );
+	lay.off_refs = align_up( lay.off_gplanes + ( uint64_t ) ogplanes.size() * sizeof( PlaneRec ), kSectionAlign );
+	lay.off_sides_even = align_up( lay.off_refs + ( uint64_t ) orefs.size() * sizeof( BrushRef ), kSectionAlign );
+	lay.off_sides_odd = align_up( lay.off_sides_even + half_bytes, kSectionAlign );
+	lay.staged_bytes = align_up( lay.off_sides_odd + half_bytes, kSectionAlign );
+	lay.off_side_pairs = lay.staged_bytes;
+	lay.off_side_plane = align_up( lay.off_side_pairs + ( uint64_t ) num_sides_out * sizeof( SideRec ), kSectionAlign );
+	lay.off_node_orig = align_up( lay.off_side_plane + ( uint64_t ) num_sides_out * sizeof( uint32_t ), kSectionAlign );
+	lay.off_leaf_cluster = align_up( lay.off_node_orig + ( uint64_t ) num_nodes * sizeof( NodeOrig ), kSectionAlign );
+	lay.off_grid = align_up( lay.off_leaf_cluster + ( uint64_t ) L.num_leaves * sizeof( int32_t ), kSectionAlign );
 
 	/* ---- start grid (map_layout.h).  World box = the root node's bounds (reference bsp.h:63-64 mins/maxs, unused
 	 *      by the reference's trace); no grid when a map does not carry them. */
@@ -239,8 +220,9 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 			if( fabs( ( double ) root.mins[ a ] ) > scale ) scale = fabs( ( double ) root.mins[ a ] );
 			if( fabs( ( double ) root.maxs[ a ] ) > scale ) scale = fabs( ( double ) root.maxs[ a ] );
 		}
+		ok = ok && opt.grid_cells != 0;
 		for( uint32_t i = 0; ok && i < num_nodes; i++ ) {
-			const NodeRec & n = onodes[ i ];
+			const PlaneRec & n = full_planes[ i ];
 			ok = ok && std::isfinite( n.nx ) && std::isfinite( n.ny ) && std::isfinite( n.nz ) && std::isfinite( n.d );
 			const double nlen = fabs( ( double ) n.nx ) + fabs( ( double ) n.ny ) + fabs( ( double ) n.nz );
 			ok = ok && nlen < 4.0;                       /* the margins below assume roughly unit normals */
@@ -249,7 +231,7 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 		if( ok ) {
 			/* ~cubic cells, about 2^20 of them (4 MB), at most 256 along an axis */
 			double target_cells = 1048576.0;
-			if( const char * env = getenv( "BSPGPU_GRID_CELLS" ) ) { const double v = atof( env ); if( v >= 1.0 && v <= 6.4e7 ) target_cells = v; }   /* tuning knob */
+			if( opt.grid_cells > 0 ) target_cells = ( double ) ( opt.grid_cells > 64000000 ? 64000000 : opt.grid_cells );   /* bspgpu_create_opts */
 			double cell = cbrt( ext[ 0 ] * ext[ 1 ] * ext[ 2 ] / target_cells );
 			int32_t dim[ 3 ];
 			for( int pass = 0; pass < 2; pass++ ) {
@@ -275,7 +257,8 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 				}
 				int32_t ref = 0;
 				for( ;; ) {
-					const NodeRec & n = onodes[ ref ];
+					const PlaneRec & n = full_planes[ ref ];
+					const NodeRec & nrec = onodes[ ref ];
 					const double nn[ 3 ] = { n.nx, n.ny, n.nz };
 					double dmin = -( double ) n.d, dmax = -( double ) n.d;
 					for( int a = 0; a < 3; a++ ) {
@@ -283,8 +266,8 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 						dmax += nn[ a ] >= 0.0 ? nn[ a ] * bhi[ a ] : nn[ a ] * blo[ a ];
 					}
 					int32_t child;
-					if( dmin >= delta ) child = n.child[ 0 ];          /* everything in front: children[ dist > 0 ] = children[ 0 ] */
-					else if( dmax <= -delta ) child = n.child[ 1 ];
+					if( dmin >= delta ) child = nrec.child[ 0 ];       /* everything in front: children[ dist > 0 ] = children[ 0 ] */
+					else if( dmax <= -delta ) child = nrec.child[ 1 ];
 					else break;
 					ref = child;
 					if( child < 0 ) break;                          /* a leaf reference or kEmptyLeaf */
@@ -303,18 +286,23 @@ int flatten_map( const bspgpu_map_desc & L, FlatMap & out, std::string & err ) {
 	if( lay.total_bytes == 0 ) lay.total_bytes = kSectionAlign;
 
 	out.image.assign( lay.total_bytes, 0 );
-	memcpy( out.image.data() + lay.off_nodes, onodes.data(), onodes.size() * sizeof( NodeRec ) );
-	if( !orefs.empty() ) memcpy( out.image.data() + lay.off_refs, orefs.data(), orefs.size() * sizeof( BrushRef ) );
-	memcpy( out.image.data() + lay.off_qnodes, qnodes.data(), qnodes.size() * sizeof( QNodeRec ) );
+	unsigned char * img = out.image.data();
+	memcpy( img + lay.off_nodes, onodes.data(), onodes.size() * sizeof( NodeRec ) );
+	if( !ogplanes.empty() ) memcpy( img + lay.off_gplanes, ogplanes.data(), ogplanes.size() * sizeof( PlaneRec ) );
+	if( !orefs.empty() ) memcpy( img + lay.off_refs, orefs.data(), orefs.size() * sizeof( BrushRef ) );
 	if( !osides.empty() ) {
-		memcpy( out.image.data() + lay.off_sides, osides.data(), osides.size() * sizeof( SideRec ) );
-		memcpy( out.image.data() + lay.off_side_plane, oside_plane.data(), oside_plane.size() * sizeof( uint32_t ) );
+		memcpy( img + lay.off_side_pairs, osides.data(), osides.size() * sizeof( SideRec ) );
+		memcpy( img + lay.off_side_plane, oside_plane.data(), oside_plane.size() * sizeof( uint32_t ) );
+		SideRec * even = ( SideRec * ) ( img + lay.off_sides_even ), * odd = ( SideRec * ) ( img + lay.off_sides_odd );
+		for( size_t k = 0; k + 1 < osides.size(); k += 2 ) { even[ k / 2 ] = osides[ k ]; odd[ k / 2 ] = osides[ k + 1 ]; }
 	}
-	if( !grid_cells.empty() ) memcpy( out.image.data() + lay.off_grid, grid_cells.data(), grid_cells.size() * sizeof( int32_t ) );
+	memcpy( img + lay.off_node_orig, oorig.data(), oorig.size() * sizeof( NodeOrig ) );
+	for( uint32_t i = 0; i < L.num_leaves; i++ ) memcpy( img + lay.off_leaf_cluster + ( uint64_t ) i * 4, &leaves[ i ].cluster, 4 );
+	if( !grid_cells.empty() ) memcpy( img + lay.off_grid, grid_cells.data(), grid_cells.size() * sizeof( int32_t ) );
 	return BSPGPU_OK;
 }
 
-int read_ibsp_file( const char * path, std::vector< unsigned char > & blob, bspgpu_map_desc & lumps, std::string & err ) {
+int read_ibsp_file( const char * path, std::vector< unsigned char > & blob, bspgpu_map_desc & lumps, const void ** vis, uint64_t * vis_len, std::string & err ) {
 	FILE * f = fopen( path, "rb" );
 	if( !f ) { err = std::string( "cannot open " ) + path; return BSPGPU_E_IO; }
 	fseek( f, 0, SEEK_END );
@@ -346,6 +334,12 @@ int read_ibsp_file( const char * path, std::vector< unsigned char > & blob, bspg
 		if( ( uint64_t ) d.off + d.len > ( uint64_t ) len ) { err = std::string( w.name ) + ": lump runs past end of file"; return BSPGPU_E_MAP; }
 		*w.ptr = blob.data() + d.off;
 		*w.count = ( uint32_t ) ( d.len / w.elem );
+	}
+	if( vis ) {
+		const Dirent & d = dir[ 16 ];   /* LUMP_VISIBILITY (bsp.h:24) */
+		if( ( uint64_t ) d.off + d.len > ( uint64_t ) len ) { err = "visibility: lump runs past end of file"; return BSPGPU_E_MAP; }
+		*vis = blob.data() + d.off;
+		*vis_len = d.len;
 	}
 	return BSPGPU_OK;
 }

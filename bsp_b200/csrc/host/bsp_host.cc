@@ -50,14 +50,22 @@ void bsp_init( BSP * bsp, std::string filename, int device ) {
 	if( fread( bsp->contents, 1, ( size_t ) len, f ) != ( size_t ) len ) { fprintf( stderr, "bsp: short read on %s\n", filename.c_str() ); abort(); }
 	fclose( f );
 
-	/* directory slots: 1 textures, 2 planes, 3 nodes, 4 leaves, 6 leafbrushes, 8 brushes, 9 brushsides (bsp.h:7-27) */
+	/* the eleven lumps of bsp_init (bsp.cc:74-84; directory slots per bsp.h:7-27) + load_vis (bsp.cc:105-114) */
 	point_lump( bsp, len, 1, bsp->num_textures, bsp->textures, "textures" );
 	point_lump( bsp, len, 2, bsp->num_planes, bsp->planes, "planes" );
 	point_lump( bsp, len, 3, bsp->num_nodes, bsp->nodes, "nodes" );
 	point_lump( bsp, len, 4, bsp->num_leaves, bsp->leaves, "leaves" );
+	point_lump( bsp, len, 5, bsp->num_leaf_faces, bsp->leaf_faces, "leaffaces" );
 	point_lump( bsp, len, 6, bsp->num_leaf_brushes, bsp->leaf_brushes, "leafbrushes" );
 	point_lump( bsp, len, 8, bsp->num_brushes, bsp->brushes, "brushes" );
 	point_lump( bsp, len, 9, bsp->num_brush_sides, bsp->brush_sides, "brushsides" );
+	point_lump( bsp, len, 10, bsp->num_vertices, bsp->vertices, "vertices" );
+	point_lump( bsp, len, 11, bsp->num_mesh_verts, bsp->mesh_verts, "meshverts" );
+	point_lump( bsp, len, 13, bsp->num_faces, bsp->faces, "faces" );
+	const Dirent & vd = reinterpret_cast< const Dirent * >( bsp->contents + 8 )[ 16 ];
+	if( ( uint64_t ) vd.off + vd.len > ( uint64_t ) len || vd.len < 8 ) { fprintf( stderr, "bsp: visibility lump is malformed (off %u len %u)\n", vd.off, vd.len ); abort(); }
+	bsp->vis = reinterpret_cast< BSP_Vis * >( bsp->contents + vd.off );
+	if( vd.len != 8 + ( uint64_t ) bsp->vis->num_clusters * bsp->vis->cluster_size ) { fprintf( stderr, "bsp: visibility lump length does not match its header (bsp.cc:111)\n" ); abort(); }
 
 	bspgpu_map_desc d;
 	d.textures = bsp->textures;         d.num_textures = bsp->num_textures;
@@ -67,8 +75,18 @@ void bsp_init( BSP * bsp, std::string filename, int device ) {
 	d.leaf_brushes = bsp->leaf_brushes; d.num_leaf_brushes = bsp->num_leaf_brushes;
 	d.brushes = bsp->brushes;           d.num_brushes = bsp->num_brushes;
 	d.brush_sides = bsp->brush_sides;   d.num_brush_sides = bsp->num_brush_sides;
+	if( device == BSP_ALL_GPUS ) {
+		check( bspgpu_multi_create( &bsp->multi, &d, nullptr, 0 ), "bspgpu_multi_create" );
+		for( int r = 0; r < bspgpu_multi_device_count( bsp->multi ); r++ )
+			check( bspgpu_set_vis( bspgpu_multi_handle( bsp->multi, r ), bsp->vis, vd.len ), "bspgpu_set_vis" );
+		return;
+	}
 	check( bspgpu_create( &bsp->gpu, &d, device ), "bspgpu_create" );
+	check( bspgpu_set_vis( bsp->gpu, bsp->vis, vd.len ), "bspgpu_set_vis" );
 }
+
+/* point queries and device-pointer calls go to one replica */
+static bspgpu_t * one_gpu( const BSP * bsp ) { return bsp->gpu ? bsp->gpu : bspgpu_multi_handle( bsp->multi, 0 ); }
 
 void bsp_init( BSP * bsp, std::string filename ) {
 	bsp_init( bsp, filename, -1 );
@@ -76,20 +94,26 @@ void bsp_init( BSP * bsp, std::string filename ) {
 
 void bsp_destroy( BSP * bsp ) {
 	bspgpu_destroy( bsp->gpu );
-	bsp->gpu = nullptr;
+	bspgpu_multi_destroy( bsp->multi );
+	bsp->gpu = nullptr; bsp->multi = nullptr;
 	delete[] bsp->contents;
 	bsp->contents = nullptr;
 }
 
 void BSP::trace_segs( const Segment * segs, size_t n, TraceResult * out ) const {
 	static_assert( sizeof( Segment ) == 24, "Segment is two packed vec3" );
-	check( bspgpu_trace( gpu, segs, n, out, BSPGPU_SEGS_PACKED24 ), "bspgpu_trace" );
+	if( multi ) check( bspgpu_multi_trace( multi, segs, n, out, nullptr, BSPGPU_SEGS_PACKED24 ), "bspgpu_multi_trace" );
+	else check( bspgpu_trace( gpu, segs, n, out, BSPGPU_SEGS_PACKED24 ), "bspgpu_trace" );
 }
 
 void BSP::trace_segs( const Segment * segs, size_t n, Intersection * is, bool * hit ) const {
-	std::vector< TraceResult > res( n );
-	std::vector< bspgpu_pos > pos( n );
-	check( bspgpu_trace_pos( gpu, segs, n, res.data(), pos.data(), BSPGPU_SEGS_PACKED24 ), "bspgpu_trace_pos" );
+	/* a batch of one (trace_seg) or a handful: no heap traffic */
+	TraceResult res_small[ 16 ]; bspgpu_pos pos_small[ 16 ];
+	std::vector< TraceResult > res_big; std::vector< bspgpu_pos > pos_big;
+	TraceResult * res = res_small; bspgpu_pos * pos = pos_small;
+	if( n > 16 ) { res_big.resize( n ); pos_big.resize( n ); res = res_big.data(); pos = pos_big.data(); }
+	if( multi ) check( bspgpu_multi_trace( multi, segs, n, res, pos, BSPGPU_SEGS_PACKED24 ), "bspgpu_multi_trace" );
+	else check( bspgpu_trace_pos( gpu, segs, n, res, pos, BSPGPU_SEGS_PACKED24 ), "bspgpu_trace_pos" );
 	for( size_t i = 0; i < n; i++ ) {
 #ifdef BSP_HOST_FILL_PLANE
 		is[ i ].plane = res[ i ].plane >= 0 ? &planes[ res[ i ].plane ] : nullptr;
@@ -111,13 +135,12 @@ bool BSP::trace_seg( const glm::vec3 & start, const glm::vec3 & end, Intersectio
 }
 
 void BSP::trace_segs_device( const bspgpu_segment * d_segs, size_t n, TraceResult * d_out, void * cuda_stream ) const {
-	check( bspgpu_set_stream( gpu, cuda_stream ), "bspgpu_set_stream" );
-	check( bspgpu_trace( gpu, d_segs, n, d_out, BSPGPU_SEGS_DEVICE | BSPGPU_OUT_DEVICE | BSPGPU_ASYNC ), "bspgpu_trace" );
-	check( bspgpu_reset_stream( gpu ), "bspgpu_reset_stream" );
+	/* one call, its own stream argument: nothing of the handle's state changes, two threads cannot interleave a set / reset */
+	check( bspgpu_trace_stream( one_gpu( this ), d_segs, n, d_out, nullptr, BSPGPU_SEGS_DEVICE | BSPGPU_OUT_DEVICE | BSPGPU_ASYNC, cuda_stream ), "bspgpu_trace_stream" );
 }
 
 void BSP::positions_to_leaves( const glm::vec3 * pos, size_t n, int32_t * leaf ) const {
-	check( bspgpu_leaf( gpu, reinterpret_cast< const float * >( pos ), 3, n, leaf, 0 ), "bspgpu_leaf" );
+	check( bspgpu_leaf( one_gpu( this ), reinterpret_cast< const float * >( pos ), 3, n, leaf, 0 ), "bspgpu_leaf" );
 }
 
 BSP_Leaf & BSP::position_to_leaf( const glm::vec3 & pos ) const {
@@ -126,8 +149,14 @@ BSP_Leaf & BSP::position_to_leaf( const glm::vec3 & pos ) const {
 	return leaves[ leaf ];
 }
 
+void BSP::visible_leaves( const glm::vec3 & pos, uint8_t * visible ) const {
+	const float p[ 3 ] = { pos.x, pos.y, pos.z };
+	check( bspgpu_visible_leaves( one_gpu( this ), p, visible, nullptr ), "bspgpu_visible_leaves" );
+}
+
 uint64_t BSP::last_hit_count() const {
 	uint64_t hits = 0;
-	check( bspgpu_hit_count( gpu, &hits ), "bspgpu_hit_count" );
+	if( multi ) check( bspgpu_multi_hit_count( multi, &hits ), "bspgpu_multi_hit_count" );   /* NCCL all-reduce of the per-GPU counters */
+	else check( bspgpu_hit_count( gpu, &hits ), "bspgpu_hit_count" );
 	return hits;
 }

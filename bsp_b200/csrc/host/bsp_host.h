@@ -28,6 +28,7 @@
 
 #include "vec3.h"
 #include "../../../include/bspgpu.h"
+#include "../../../include/bspgpu_multi.h"
 
 /* ---- Quake-3 IBSP v46 records as they sit in the file (reference bsp.h:41-96) ---- */
 struct BSP_Texture { char name[ 64 ]; int32_t surface_flags; int32_t content_flags; };
@@ -39,12 +40,26 @@ struct BSP_Leaf {
 	uint32_t first_face, num_faces;
 	uint32_t first_brush, num_brushes;
 };
+typedef uint32_t BSP_LeafFace;
 typedef uint32_t BSP_LeafBrush;
 struct BSP_Brush { uint32_t first_side, num_sides; int32_t texture; };
 struct BSP_BrushSide { uint32_t plane; int32_t texture; };
+/* render-side records (reference bsp.h:98-127): not read by the trace, kept so that code written against the
+ * reference's BSP -- bsp_renderer.cc walks leaf_faces, faces, vertices, mesh_verts and vis -- compiles unchanged */
+struct BSP_Vertex { glm::vec3 pos; float uv[ 2 ][ 2 ]; glm::vec3 normal; uint8_t rgba[ 4 ]; };
+typedef int32_t BSP_MeshVert;
+struct BSP_Face {
+	int32_t texture, effect, type;
+	int32_t first_vert, num_verts, first_mesh_vert, num_mesh_verts;
+	int32_t lightmap, lmpos[ 2 ], lmsize[ 2 ];
+	glm::vec3 lmorigin, a, b, normal;
+	int32_t c, d;
+};
+struct BSP_Vis { uint32_t num_clusters, cluster_size; uint8_t pvs[ 1 ]; };   /* the reference declares a flexible array, bsp.h:129-134 */
 
 static_assert( sizeof( BSP_Texture ) == 72 && sizeof( BSP_Plane ) == 16 && sizeof( BSP_Node ) == 36, "IBSP layout" );
 static_assert( sizeof( BSP_Leaf ) == 48 && sizeof( BSP_Brush ) == 12 && sizeof( BSP_BrushSide ) == 8, "IBSP layout" );
+static_assert( sizeof( BSP_Vertex ) == 44 && sizeof( BSP_Face ) == 104, "IBSP layout" );
 
 /* result of one trace, reference bsp.h:143-147.  `plane` stays null exactly as in the
  * reference (bsp.cc:256,268 never assign it) unless BSP_HOST_FILL_PLANE is defined. */
@@ -67,15 +82,22 @@ class BSP {
 public:
 	char * contents;
 
+	/* same members, same order as the reference (bsp.h:160-193) */
 	uint32_t num_textures;      BSP_Texture * textures;
 	uint32_t num_planes;        BSP_Plane * planes;
 	uint32_t num_nodes;         BSP_Node * nodes;
 	uint32_t num_leaves;        BSP_Leaf * leaves;
+	uint32_t num_leaf_faces;    BSP_LeafFace * leaf_faces;
 	uint32_t num_leaf_brushes;  BSP_LeafBrush * leaf_brushes;
 	uint32_t num_brushes;       BSP_Brush * brushes;
 	uint32_t num_brush_sides;   BSP_BrushSide * brush_sides;
+	uint32_t num_vertices;      BSP_Vertex * vertices;
+	uint32_t num_mesh_verts;    BSP_MeshVert * mesh_verts;
+	uint32_t num_faces;         BSP_Face * faces;
+	BSP_Vis * vis;
 
-	bspgpu_t * gpu;             /* opaque: flattened map + streams on the device */
+	bspgpu_t * gpu;             /* opaque: flattened map + streams on one device (null when the map lives on several) */
+	bspgpu_multi_t * multi;     /* opaque: one replica per GPU of the box (bsp_init with device == BSP_ALL_GPUS) */
 
 	/* reference API */
 	bool trace_seg( const glm::vec3 & start, const glm::vec3 & end, Intersection & is ) const;
@@ -90,12 +112,16 @@ public:
 	void trace_segs_device( const bspgpu_segment * d_segs, size_t n, TraceResult * d_out, void * cuda_stream ) const;
 	/* batched position_to_leaf: leaf index per point */
 	void positions_to_leaves( const glm::vec3 * pos, size_t n, int32_t * leaf ) const;
+	/* which leaves bspr_render would draw from `pos` (bsp_renderer.cc:147-168): visible[ num_leaves ] */
+	void visible_leaves( const glm::vec3 & pos, uint8_t * visible ) const;
 	/* hits of the last trace_segs call */
 	uint64_t last_hit_count() const;
 };
 
 void bsp_init( BSP * bsp, std::string filename );
-/* device < 0: current CUDA device */
+/* device >= 0: that GPU; BSP_CURRENT_GPU: the calling thread's current CUDA device; BSP_ALL_GPUS: the map is replicated on every
+ * GPU of the box and trace_segs shards its segments across them (contiguous ranges, results in place) */
+enum { BSP_CURRENT_GPU = -1, BSP_ALL_GPUS = -2 };
 void bsp_init( BSP * bsp, std::string filename, int device );
 void bsp_destroy( BSP * bsp );
 

@@ -6,19 +6,33 @@
  * 8 of 48 and 4 of 72 bytes of the records it touches.  The device image keeps only what
  * the trace reads and removes every second hop:
  *
- *   NodeRec  (32 B)  split plane embedded + both children; nodes in breadth-first order so
- *                    the top of the tree is one contiguous prefix (staged in shared memory).
+ *   NodeRec  (16 B)  split-plane distance + both children + `w`.  Nodes are in breadth-first order.
  *                    child >= 0: node index; child == kEmptyLeaf: leaf without solid brushes;
  *                    otherwise ~child = index of the leaf's first BrushRef.
+ *                    w = 0/1/2: the plane normal is bitwise +e_x / +e_y / +e_z (every node of a kd-style
+ *                    map, most nodes of a q3map tree): the walk then needs no normal at all -- for a ray
+ *                    whose six components are finite and whose start components are non-zero,
+ *                    dot(start, e_a) and dot(e_a, dir) evaluated the reference's way are bitwise start.a
+ *                    and dir.a (trace_core.h: ray_is_plain; other rays take the general arithmetic).
+ *                    w >= kGeneralPlane: normal = gplanes[ w - kGeneralPlane ] (one more 16-byte fetch).
+ *   PlaneRec (16 B)  (n.xyz, d): the general node planes, and the brush sides.
  *   BrushRef (16 B)  one per (leaf, solid brush): side range + brush index; the leaf's last
  *                    entry carries kLastRef, so no leaf record and no count are needed.
  *                    The content test (textures[brush.texture].content_flags & 1, bsp.cc:193)
  *                    is baked in: non-solid brushes are dropped at flatten time.
- *   SideRec  (16 B)  the side's plane embedded (n.xyz, d), indexed like the brushsides lump.
+ *   sides            re-laid out per solid brush: even start, even count (zero-normal, d = +inf padding
+ *                    sides are a no-op for every input), so a leaf step clips TWO sides per fetch.
+ *                    Stored twice: `side_pairs` (sides 2k, 2k+1 adjacent: ONE 256-bit gather on the
+ *                    read-only path) and `sides_even | sides_odd` (two dense 16-byte arrays: when the map
+ *                    is staged in shared memory a dense array spreads eight lanes over eight bank groups,
+ *                    the 32-byte-stride pair layout only over four -- ncu round 1: 57 % of the shared-memory
+ *                    wavefronts of the staged kernel were bank conflicts).
  *   side_plane (4 B) planes-lump index per side, read once per hit for the `plane` extension.
+ *   node_orig  (8 B) the file's own child values per node, read only by batched position_to_leaf.
+ *   leaf_cluster (4 B) BSP_Leaf::cluster per leaves-lump index (bsp.h:68), for the PVS lookup.
  *
- * One device allocation holds [nodes | refs | sides | side_plane | qnodes | start grid], each section
- * 128-byte aligned; the whole-map shared-memory variant copies the first three sections verbatim.
+ * One device allocation; sections 128-byte aligned.  [nodes | gplanes | refs | sides_even | sides_odd] is a
+ * contiguous prefix that the shared-memory variant copies verbatim (TMA bulk copy).
  */
 #ifndef BSPGPU_MAP_LAYOUT_H
 #define BSPGPU_MAP_LAYOUT_H
@@ -28,41 +42,26 @@
 namespace bspk {
 
 struct alignas( 16 ) NodeRec {
-	float nx, ny, nz, d;
+	float d;
 	int32_t child[ 2 ];      /* [0] front (dist >= 0 side), [1] back -- same slot order as the reference */
+	uint32_t w;              /* 0,1,2 = axis of a bitwise +unit normal; >= kGeneralPlane = gplanes index + kGeneralPlane */
+};
+static const uint32_t kGeneralPlane = 4;
+
+struct alignas( 16 ) PlaneRec {
+	float nx, ny, nz, d;
+};
+typedef PlaneRec SideRec;
+
+struct NodeOrig {
 	int32_t orig_child[ 2 ]; /* the file's own child values (leaf = -(idx+1)), for position_to_leaf */
 };
 
-/* QNodeRec (32 B): the record the read-only-path walk fetches -- ONE scattered 256-bit gather per visit, and for
- * axis-aligned split planes (every node plane of a kd-style map; q3map prefers them too) that one gather carries
- * TWO tree levels: the node's plane distance, both children's plane distances and the four grandchildren.
- *   general  words 0-3 plane (n.xyz, d), 4-5 children, 6 unused, 7 = 0
- *   packed   words 0-2 d of the node / of child 0 / of child 1, words 3-6 g0..g3, word 7 = w:
- *              bit 0      = 1 (packed)
- *              bit 1,2    child 0 / child 1 is "expanded": an internal node with an axial plane whose own d is in
- *                         word 1 / 2 and whose children are g0,g1 / g2,g3.  A child that is not expanded keeps its
- *                         ordinary reference in g0 / g2.
- *              bits 3-4, 5-6, 7-8   axis (0 x, 1 y, 2 z) of the node's, child 0's, child 1's plane
- *              bits 9-31  node index of the first expanded child; the second expanded child is the next index
- *                         (children are numbered consecutively in breadth-first order)
- * Only planes whose normal is bitwise (+1,+0,+0) / (+0,+1,+0) / (+0,+0,+1) are packed; the kernel rebuilds exactly
- * that normal and runs the same arithmetic as for a general record, so packing never changes a result.  Every node
- * keeps its own record at its own index (pops and start-grid references land there). */
-struct alignas( 32 ) QNodeRec {
-	uint32_t w[ 8 ];
-};
-static const uint32_t kQPacked = 1u, kQExpand0 = 2u, kQExpand1 = 4u;
-static const uint32_t kQAxisShift = 3, kQAxis0Shift = 5, kQAxis1Shift = 7, kQBaseShift = 9;
-
 struct alignas( 16 ) BrushRef {
-	uint32_t first_side;
-	uint32_t num_sides;      /* bit 31 (kLastRef) = last solid brush of this leaf */
+	uint32_t first_side;     /* even */
+	uint32_t num_sides;      /* even; bit 31 (kLastRef) = last solid brush of this leaf */
 	int32_t brush;           /* brushes-lump index */
 	uint32_t reserved;
-};
-
-struct alignas( 16 ) SideRec {
-	float nx, ny, nz, d;
 };
 
 static const int32_t kEmptyLeaf = INT32_MIN;
@@ -82,9 +81,10 @@ struct StartGridDesc {
 
 /* byte offsets of the sections inside the single device image */
 struct MapImageLayout {
-	uint32_t num_nodes, num_refs, num_sides, tree_depth;
-	uint64_t off_nodes, off_refs, off_sides, off_side_plane, off_qnodes, off_grid, total_bytes;
-	uint64_t staged_bytes;   /* prefix [nodes|refs|sides] the whole-map variant copies to shared memory */
+	uint32_t num_nodes, num_gplanes, num_refs, num_sides, tree_depth, num_leaves;
+	uint64_t off_nodes, off_gplanes, off_refs, off_sides_even, off_sides_odd;   /* the staged prefix */
+	uint64_t off_side_pairs, off_side_plane, off_node_orig, off_leaf_cluster, off_grid, total_bytes;
+	uint64_t staged_bytes;   /* prefix the whole-map variant copies to shared memory */
 	StartGridDesc grid;
 };
 

@@ -14,6 +14,17 @@
  * single IEEE-754 rounding in the reference's order: build with -fmad=false -prec-div=true
  * -ftz=false (nvcc) / -ffp-contract=off (g++).  glm::dot(vec3) is (x*x' + y*y') + z*z'.
  *
+ * Node planes whose normal is bitwise +e_x / +e_y / +e_z carry only their axis (map_layout.h: NodeRec).  Two ways to
+ * evaluate them, both exact:
+ *   general  rebuild the unit normal and run the same dot products as for any plane (node_plane_exact): bit-identical
+ *            to the reference for EVERY input, because it is the reference's arithmetic;
+ *   plain    for a ray whose six components are finite and whose start components are non-zero (ray_is_plain),
+ *            (s.x*1 + s.y*0) + s.z*0 is bitwise s.x (adding +-0 to a non-zero finite number changes nothing) and
+ *            (1*d.x + 0*d.y) + 0*d.z is d.x up to the sign of a zero, which no comparison and no stored value can
+ *            see (a zero denominator fails `denom != 0`, bsp.cc:226).  The resumable walk the kernels run uses this
+ *            form; rays that are not plain (NaN / infinite / zero start coordinates) are traced start to finish with
+ *            the general form instead (trace_one), so the result is the reference's in both cases.
+ *
  * Stack invariant of the simple form trace_one (lets an entry be 8 bytes; the resumable form the shipped kernel
  * runs stores its intervals explicitly, see below): the reference's far call gets [t, tmax] where
  * tmax is the interval end of the node that straddled (bsp.cc:250-252).  At any moment the
@@ -81,12 +92,28 @@ BSPK_HD int32_t node_step( const Ray & r, float nx, float ny, float nz, float d,
 	return near_child ? c1 : c0;                                               /* children[ near ] :248 */
 }
 
+/* plane and children of node i with the normal spelled out: an axis record becomes the exact unit normal it stands for */
+template< class Map >
+BSPK_HD void node_plane_exact( const Map & map, int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) {
+	uint32_t w;
+	map.node( i, d, c0, c1, w );
+	if( w < kGeneralPlane ) { nx = w == 0u ? 1.0f : 0.0f; ny = w == 1u ? 1.0f : 0.0f; nz = w == 2u ? 1.0f : 0.0f; }
+	else map.gplane( w - kGeneralPlane, nx, ny, nz );
+}
+
+/* see the header: dot(start, e_a) == start.a and dot(e_a, dir) == dir.a (up to the sign of a zero denominator) bit for bit */
+BSPK_HD bool ray_is_plain( const Ray & r ) {
+	const float p = ( r.sx * r.sy ) * r.sz;   /* finite and non-zero => every start component is finite and non-zero */
+	const float q = ( r.dx * r.dy ) * r.dz;   /* finite => every direction component is finite (inf * 0 = NaN) */
+	return fabsf( p ) > 0.0f && fabsf( p ) < INFINITY && fabsf( q ) < INFINITY;
+}
+
 /* trace_seg_tree from `node` down to a leaf reference; pending far sides go on the stack. */
 template< class Map >
 BSPK_HD int32_t descend( const Map & map, const Ray & r, int32_t node, float tmin, float & tmax, StackEntry * stack, int32_t & sp ) {
 	while( node >= 0 ) {
 		float nx, ny, nz, d; int32_t c0, c1;
-		map.node( node, nx, ny, nz, d, c0, c1 );
+		node_plane_exact( map, node, nx, ny, nz, d, c0, c1 );
 		int32_t far; bool both;
 		node = node_step( r, nx, ny, nz, d, c0, c1, tmin, tmax, far, both );
 		if( both ) {
@@ -325,11 +352,8 @@ BSPK_HD void lane_hit_state( const Lane & l, HitState & h ) {
  *   near child has work            -> go there over [tmin, u or tmax]; push the far child over [u, tmax] if it has work
  *   near child is an empty leaf    -> go straight to the far child over [u, tmax] if the segment straddles and it has work
  *   neither                        -> next pending far side from the stack (the second recursive call, :250-252), or done */
-/* returns the child slot the walk continued into (0 front, 1 back), or 2 when it continued from the stack / finished */
 template< class Stack >
-BSPK_HD int32_t lane_node_apply( Lane & l, const Stack & stack, float nx, float ny, float nz, float d, int32_t c0, int32_t c1 ) {
-	const float denom = dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );                /* :220 */
-	const float dist = -( dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d );        /* :221 */
+BSPK_HD void lane_node_apply( Lane & l, const Stack & stack, float denom, float dist, int32_t c0, int32_t c1 ) {
 	const float u = dist / denom;                                                  /* :227 */
 	const bool in_range = denom != 0.0f && u >= 0.0f && u <= l.tmax;               /* :226,:232 */
 	const bool below = u < l.tmin;                                                 /* :235 */
@@ -355,47 +379,25 @@ BSPK_HD int32_t lane_node_apply( Lane & l, const Stack & stack, float nx, float 
 		l.sp--;
 		stack_get( stack, l.sp, l.cur, l.tmin, l.tmax );
 	}
-	return do_pop ? 2 : ( ( near_back == near_ok ) ? 1 : 0 );                      /* near taken: slot near_back; far taken: the other one */
 }
 
+/* the lane's ray must be plain (ray_is_plain) */
 template< class Map, class Stack >
 BSPK_HD void lane_node_step( const Map & map, Lane & l, const Stack & stack ) {
-	float nx, ny, nz, d; int32_t c0, c1;
-	map.node( l.cur, nx, ny, nz, d, c0, c1 );
-	lane_node_apply( l, stack, nx, ny, nz, d, c0, c1 );
-}
-
-BSPK_HD float bits_to_float( uint32_t u ) {
-#ifdef __CUDA_ARCH__
-	return __uint_as_float( u );
-#else
-	float f; memcpy( &f, &u, 4 ); return f;
-#endif
-}
-
-/* the same step on a QNodeRec (map_layout.h): one record fetch, one or two tree levels.  A packed record's plane is
- * rebuilt as the exact unit normal it stands for and goes through lane_node_apply like any other plane, so the
- * arithmetic -- and the result -- is that of two lane_node_steps; only the second record fetch is gone. */
-template< class Map, class Stack >
-BSPK_HD void lane_qnode_step( const Map & map, Lane & l, const Stack & stack ) {
-	uint32_t q0, q1, q2, q3, q4, q5, q6, w;
-	map.qnode( l.cur, q0, q1, q2, q3, q4, q5, q6, w );
-	if( !( w & kQPacked ) ) {
-		lane_node_apply( l, stack, bits_to_float( q0 ), bits_to_float( q1 ), bits_to_float( q2 ), bits_to_float( q3 ), ( int32_t ) q4, ( int32_t ) q5 );
-		return;
+	float d; int32_t c0, c1; uint32_t w;
+	map.node( l.cur, d, c0, c1, w );
+	float denom, sdot;
+	if( w < kGeneralPlane ) {
+		sdot = w == 0u ? l.r.sx : ( w == 1u ? l.r.sy : l.r.sz );                   /* = dot( start, e_w ), :221 */
+		denom = w == 0u ? l.r.dx : ( w == 1u ? l.r.dy : l.r.dz );                  /* = dot( e_w, dir ),   :220 */
 	}
-	const uint32_t base = w >> kQBaseShift;
-	const bool e0 = ( w & kQExpand0 ) != 0, e1 = ( w & kQExpand1 ) != 0;
-	const uint32_t ax = ( w >> kQAxisShift ) & 3u;
-	const int32_t c0 = e0 ? ( int32_t ) base : ( int32_t ) q3;
-	const int32_t c1 = e1 ? ( int32_t ) ( base + ( e0 ? 1u : 0u ) ) : ( int32_t ) q5;
-	const int32_t took = lane_node_apply( l, stack, ax == 0u ? 1.0f : 0.0f, ax == 1u ? 1.0f : 0.0f, ax == 2u ? 1.0f : 0.0f, bits_to_float( q0 ), c0, c1 );
-	const bool second = took == 0 ? e0 : ( took == 1 ? e1 : false );
-	if( second ) {
-		const uint32_t ax2 = ( w >> ( took ? kQAxis1Shift : kQAxis0Shift ) ) & 3u;
-		lane_node_apply( l, stack, ax2 == 0u ? 1.0f : 0.0f, ax2 == 1u ? 1.0f : 0.0f, ax2 == 2u ? 1.0f : 0.0f,
-		                 bits_to_float( took ? q2 : q1 ), ( int32_t ) ( took ? q5 : q3 ), ( int32_t ) ( took ? q6 : q4 ) );
+	else {
+		float nx, ny, nz;
+		map.gplane( w - kGeneralPlane, nx, ny, nz );
+		denom = dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );                        /* :220 */
+		sdot = dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz );
 	}
+	lane_node_apply( l, stack, denom, -( sdot - d ), c0, c1 );                     /* dist, :221 */
 }
 
 /* up to `max_steps` node steps; stops early when the lane leaves node mode */
@@ -403,8 +405,7 @@ template< class Map, class Stack >
 BSPK_HD void lane_node_phase( const Map & map, Lane & l, const Stack & stack, uint32_t max_steps ) {
 	if( !lane_in_node( l ) ) return;
 	for( ; max_steps > 0 && lane_in_node( l ); max_steps-- ) {
-		if constexpr( Map::kPackedNodes ) lane_qnode_step( map, l, stack );
-		else lane_node_step( map, l, stack );
+		lane_node_step( map, l, stack );
 	}
 	l.s = 0; l.s_end = 0;                                                          /* if the walk reached a leaf: fetch its first brush reference */
 }
@@ -489,6 +490,11 @@ BSPK_HD void trace_one_phased( const Map & map, float sx, float sy, float sz, fl
 	StackEntry16 low[ kSplit > 0 ? kSplit : 1 ];
 	Lane l;
 	lane_start( l, sx, sy, sz, ex, ey, ez );
+	if( !ray_is_plain( l.r ) ) {                       /* as the kernels do: such a ray takes the general arithmetic start to finish */
+		r_out = l.r;
+		trace_one< Map, kStack >( map, l.r, h_out );
+		return;
+	}
 	if( grid ) lane_start_at( l, grid_start_ref( *grid, sx, sy, sz, ex, ey, ez ) );
 	while( !lane_done( l ) ) {
 		if constexpr( kSplit > 0 ) {
@@ -511,12 +517,12 @@ template< class Map >
 BSPK_HD int32_t point_leaf( const Map & map, float px, float py, float pz ) {
 	int32_t node = 0;
 	for( ;; ) {
-		float nx, ny, nz, d; int32_t c0, c1, o0, o1;
-		map.node_full( node, nx, ny, nz, d, c0, c1, o0, o1 );
+		float nx, ny, nz, d; int32_t c0, c1;
+		node_plane_exact( map, node, nx, ny, nz, d, c0, c1 );
 		const float dist = dot3( px, py, pz, nx, ny, nz ) - d;
 		const bool back = dist < 0.0f;
 		const int32_t c = back ? c1 : c0;
-		if( c < 0 ) return -( ( back ? o1 : o0 ) + 1 );
+		if( c < 0 ) return -( map.orig_child( node, back ? 1 : 0 ) + 1 );
 		node = c;
 	}
 }
@@ -549,24 +555,26 @@ BSPK_HD void make_pos( const Ray & r, const HitState & h, float & px, float & py
 
 /* plain-pointer accessor over the flattened image (global memory on the device, host memory in hostsim) */
 struct ImageMap {
-	static const bool kPackedNodes = false;
 	const NodeRec * nodes;
+	const PlaneRec * gplanes;
 	const BrushRef * refs;
-	const SideRec * sides;
-	BSPK_HD void node( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1 ) const {
+	const SideRec * side_pairs;
+	const NodeOrig * node_orig;
+	BSPK_HD void node( int32_t i, float & d, int32_t & c0, int32_t & c1, uint32_t & w ) const {
 		const NodeRec & n = nodes[ i ];
-		nx = n.nx; ny = n.ny; nz = n.nz; d = n.d; c0 = n.child[ 0 ]; c1 = n.child[ 1 ];
+		d = n.d; c0 = n.child[ 0 ]; c1 = n.child[ 1 ]; w = n.w;
 	}
-	BSPK_HD void node_full( int32_t i, float & nx, float & ny, float & nz, float & d, int32_t & c0, int32_t & c1, int32_t & o0, int32_t & o1 ) const {
-		const NodeRec & n = nodes[ i ];
-		nx = n.nx; ny = n.ny; nz = n.nz; d = n.d; c0 = n.child[ 0 ]; c1 = n.child[ 1 ]; o0 = n.orig_child[ 0 ]; o1 = n.orig_child[ 1 ];
+	BSPK_HD void gplane( uint32_t i, float & nx, float & ny, float & nz ) const {
+		const PlaneRec & p = gplanes[ i ];
+		nx = p.nx; ny = p.ny; nz = p.nz;
 	}
+	BSPK_HD int32_t orig_child( int32_t i, int k ) const { return node_orig[ i ].orig_child[ k ]; }
 	BSPK_HD void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const {
 		const BrushRef & r = refs[ i ];
 		first = r.first_side; nraw = r.num_sides; brush = r.brush;
 	}
 	BSPK_HD void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const {
-		const SideRec & s = sides[ i ];
+		const SideRec & s = side_pairs[ i ];
 		nx = s.nx; ny = s.ny; nz = s.nz; d = s.d;
 	}
 	BSPK_HD void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
@@ -575,13 +583,12 @@ struct ImageMap {
 	}
 };
 
-/* same, walking the two-level QNodeRec section (map_layout.h) */
-struct ImageMapPacked : ImageMap {
-	static const bool kPackedNodes = true;
-	const QNodeRec * qnodes;
-	BSPK_HD void qnode( int32_t i, uint32_t & q0, uint32_t & q1, uint32_t & q2, uint32_t & q3, uint32_t & q4, uint32_t & q5, uint32_t & q6, uint32_t & w ) const {
-		const QNodeRec & q = qnodes[ i ];
-		q0 = q.w[ 0 ]; q1 = q.w[ 1 ]; q2 = q.w[ 2 ]; q3 = q.w[ 3 ]; q4 = q.w[ 4 ]; q5 = q.w[ 5 ]; q6 = q.w[ 6 ]; w = q.w[ 7 ];
+/* hostsim's model of the shared-memory accessor: sides come from the split even / odd arrays */
+struct ImageMapSplit : ImageMap {
+	const SideRec * sides_even, * sides_odd;
+	BSPK_HD void side_pair( uint32_t i, float & n0x, float & n0y, float & n0z, float & d0, float & n1x, float & n1y, float & n1z, float & d1 ) const {
+		const SideRec & a = sides_even[ i >> 1 ], & b = sides_odd[ i >> 1 ];
+		n0x = a.nx; n0y = a.ny; n0z = a.nz; d0 = a.d; n1x = b.nx; n1y = b.ny; n1z = b.nz; d1 = b.d;
 	}
 };
 

@@ -38,6 +38,34 @@ def build(verbose: bool = False) -> None:
         print(r.stdout, r.stderr)
     if r.returncode:
         raise RuntimeError("oracle build failed")
+    build_patched_reference(verbose)
+
+
+def build_patched_reference(verbose: bool = False) -> None:
+    """oracle/_ref/patched_ref_kat: the reference's own bsp.cc / bsp.h with INTEGRATION.md's patch applied
+    (tools/apply_integration.py) + its unmodified bsp_renderer.cc, linked against libbspgpu.so -- the checker of the drop-in
+    boundary (tests/test_integration_patch.py).  Only where the reference sources and the built product library exist."""
+    import sys
+    import tempfile
+    root = os.path.dirname(HERE)
+    ref = os.environ.get("BSP_REF_DIR", "/root/reference")
+    lib = os.path.join(root, "bsp_b200", "libbspgpu.so")
+    exe = os.path.join(HERE, "_ref", "patched_ref_kat")
+    if not os.path.exists(os.path.join(ref, "bsp.cc")) or not os.path.exists(lib):
+        return
+    deps = [lib, os.path.join(root, "tools", "apply_integration.py"), os.path.join(root, "tests", "cpp", "patched_ref_kat.cc"), os.path.join(root, "include", "bspgpu.h")]
+    if os.path.exists(exe) and all(os.path.getmtime(d) <= os.path.getmtime(exe) for d in deps):
+        return
+    sys.path.insert(0, os.path.join(root, "tests"))
+    try:
+        import test_integration_patch
+        with tempfile.TemporaryDirectory() as tmp:
+            test_integration_patch.build_patched(tmp)
+    except Exception as e:  # the checker of one test: never fatal for the build
+        if verbose:
+            print("patched reference not built:", e)
+    finally:
+        sys.path.pop(0)
 
 
 def have_reference() -> bool:

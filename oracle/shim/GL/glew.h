@@ -58,4 +58,24 @@ inline void glClear( GLbitfield ) { }
 inline void glUseProgram( GLuint ) { }
 inline void glUniformMatrix4fv( GLint, GLsizei, GLboolean, const GLfloat * ) { }
 
+/* the surface of the reference's bsp_renderer.cc (tests/test_integration_patch.py compiles it, unmodified, against the
+ * patched bsp.h and links it: it must still build and bspr_init must still walk every lump it reads) */
+typedef ptrdiff_t GLsizeiptr;
+#define GL_TRIANGLES 0x0004
+#define GL_UNSIGNED_INT 0x1405
+#define GL_FLOAT 0x1406
+#define GL_ARRAY_BUFFER 0x8892
+#define GL_ELEMENT_ARRAY_BUFFER 0x8893
+#define GL_STATIC_DRAW 0x88E4
+inline void glGenVertexArrays( GLsizei n, GLuint * a ) { for( GLsizei i = 0; i < n; i++ ) a[ i ] = ( GLuint ) i + 1; }
+inline void glGenBuffers( GLsizei n, GLuint * a ) { for( GLsizei i = 0; i < n; i++ ) a[ i ] = ( GLuint ) i + 1; }
+inline void glBindVertexArray( GLuint ) { }
+inline void glBindBuffer( GLenum, GLuint ) { }
+inline void glBufferData( GLenum, GLsizeiptr, const void *, GLenum ) { }
+inline void glEnableVertexAttribArray( GLuint ) { }
+inline void glVertexAttribPointer( GLuint, GLint, GLenum, GLboolean, GLsizei, const void * ) { }
+inline void glDrawElements( GLenum, GLsizei, GLenum, const void * ) { }
+inline void glDeleteBuffers( GLsizei, const GLuint * ) { }
+inline void glDeleteVertexArrays( GLsizei, const GLuint * ) { }
+
 #endif

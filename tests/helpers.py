@@ -99,8 +99,8 @@ class HostSim:
             if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
                 subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", so] + srcs, check=True)
             lib = C.CDLL(so)
-            lib.hostsim_create.restype = C.c_void_p
-            lib.hostsim_create.argtypes = [C.c_void_p]
+            lib.hostsim_create_opts.restype = C.c_void_p
+            lib.hostsim_create_opts.argtypes = [C.c_void_p, C.c_int, C.c_int64]
             lib.hostsim_error.restype = C.c_char_p
             lib.hostsim_destroy.argtypes = [C.c_void_p]
             lib.hostsim_layout.argtypes = [C.c_void_p, C.c_void_p]
@@ -110,7 +110,8 @@ class HostSim:
             cls._lib = lib
         return cls._lib
 
-    def __init__(self, m):
+    def __init__(self, m, general_planes_only=False, grid_cells=-1):
+        """general_planes_only: flatten every node plane as a general plane (no axis shortcut); grid_cells as bspgpu_create_opts"""
         from bsp_b200.api import MapDesc
         self.l = self.lib()
         desc = MapDesc()
@@ -120,17 +121,17 @@ class HostSim:
             self._keep.append(arr)
             setattr(desc, nm, arr.ctypes.data if arr.size else None)
             setattr(desc, "num_" + nm, len(arr))
-        self.h = self.l.hostsim_create(C.byref(desc))
+        self.h = self.l.hostsim_create_opts(C.byref(desc), 1 if general_planes_only else 0, grid_cells)
         if not self.h:
             raise ValueError(self.l.hostsim_error().decode())
 
     def layout(self):
         out = np.zeros(9, np.uint64)
         self.l.hostsim_layout(self.h, out.ctypes.data)
-        return dict(zip(("nodes", "refs", "sides", "depth", "staged_bytes", "total_bytes", "grid_cells", "packed_nodes", "expanded_children"),
+        return dict(zip(("nodes", "refs", "sides", "depth", "staged_bytes", "total_bytes", "grid_cells", "general_planes", "unused"),
                         (int(v) for v in out)))
 
-    def trace(self, segs, budgets=None, grid=False, packed=False, split_stack=False):
+    def trace(self, segs, budgets=None, grid=False, split_sides=False, split_stack=False):
         from bsp_b200.api import RESULT_DT
         segs = np.ascontiguousarray(segs, np.float32)
         res = np.zeros(len(segs), RESULT_DT)
@@ -138,7 +139,7 @@ class HostSim:
         if budgets is None:
             self.l.hostsim_trace(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data)
         else:
-            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], (1 if grid else 0) | (2 if packed else 0) | (4 if split_stack else 0))
+            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], (1 if grid else 0) | (2 if split_sides else 0) | (4 if split_stack else 0))
         return res, pos
 
     def leaf(self, pts):

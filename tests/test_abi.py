@@ -10,20 +10,44 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)           # prototypes only, not the prose around them
+    return sorted(set(re.findall(r"\b(bspgpu_[a-z_0-9]+)\s*\(", text)))
+
+
 def test_header_symbols_are_exported(native):
     lib = native.load_library()
-    text = open(os.path.join(ROOT, "include", "bspgpu.h")).read()
-    declared = sorted(set(re.findall(r"\b(bspgpu_[a-z_]+)\s*\(", text)))
-    assert len(declared) >= 17
+    declared = _declared("bspgpu.h")
+    assert len(declared) >= 23
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/bspgpu.h but not exported by libbspgpu.so"
     from bsp_b200 import api
     assert sorted(api.ABI_SYMBOLS) == declared
 
 
+def test_multi_gpu_header_symbols_are_exported(native):
+    """include/bspgpu_multi.h: the in-process multi-GPU entry points and the rank/world (one process per GPU) ones;
+    NCCL itself is bound at run time, so the library loads on a box without it"""
+    lib = native.load_library()
+    declared = _declared("bspgpu_multi.h")
+    assert len(declared) == 16, declared
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/bspgpu_multi.h but not exported by libbspgpu.so"
+    out = subprocess_ldd(native.lib_path())
+    assert "libnccl" not in out and "libcudart" not in out      # no link-time dependency on NCCL; static CUDA runtime
+    from bsp_b200 import multi
+    assert sorted(multi.MULTI_SYMBOLS) == declared
+
+
+def subprocess_ldd(path):
+    import subprocess
+    return subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+
+
 def test_abi_version_and_shard_helper(native):
     lib = native.load_library()
-    assert lib.bspgpu_abi_version() == 1
+    assert lib.bspgpu_abi_version() == 2
     assert native.shard_range(10, 1, 3) == (4, 4)
     assert native.shard_range(10, 2, 3) == (8, 2)
 
@@ -32,7 +56,8 @@ def test_wire_formats(native):
     assert native.RESULT_DT.itemsize == 16
     from bsp_b200 import api
     assert C.sizeof(api.MapDesc) == 7 * 16
-    assert C.sizeof(api.Info) >= 60
+    assert C.sizeof(api.Info) >= 80
+    assert native.RESULT8_DT.itemsize == 8 and C.sizeof(api.CreateOptions) == 16
 
 
 def _has_gpu():
@@ -72,3 +97,15 @@ def test_null_arguments(native):
     assert lib.bspgpu_trace(None, None, 1, None, 0) < 0
     assert lib.bspgpu_hit_count(None, None) < 0
     lib.bspgpu_destroy(None)                      # harmless
+    assert lib.bspgpu_multi_create(None, None, None, 0) == -1
+    assert lib.bspgpu_dist_init(None, None, 0, 1) == -1
+    lib.bspgpu_multi_destroy(None)
+
+
+def test_multi_create_fails_loudly_without_a_gpu(native, maps):
+    if _has_gpu():
+        pytest.skip("a device is present")
+    from bsp_b200 import multi
+    _, path = maps("kat0")
+    with pytest.raises(native.BspGpuError, match="no CUDA device"):
+        multi.BspGpuMulti(path)

@@ -9,7 +9,7 @@ from conftest import bits
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = {"smem": 1, "toptree": 2, "global": 3}
+VARIANTS = {"smem": 1, "global": 3}
 
 
 def _segments(m, n_uniform=200_000, n_long=200_000, n_short=100_000, n_edge=16384, seed=21):
@@ -169,6 +169,138 @@ def test_position_to_leaf(native, maps, oracle_mod):
         g.close()
 
 
+def test_compact_results_and_per_call_stream(native, maps, oracle_mod):
+    """BSPGPU_OUT_COMPACT8 (8-byte records: t, flags | (plane+1) << 2) on the host and the device path, and
+    bspgpu_trace_stream: a trace enqueued on the stream that is still generating its segments sees all of them."""
+    import torch
+    m, _ = maps("rooms8")
+    segs = _segments(m, 150_000, 50_000, 20_000, 4096)
+    exp, _, _ = oracle_mod.Port(m).trace(segs)
+    want_bits = (exp["flags"] | ((exp["plane"] + 1).astype(np.uint32) << 2)).astype(np.uint32)
+    g = native.BspGpu(m)
+    g.set_option(5, 40_000)
+    r8 = g.trace(segs, compact=True)
+    assert r8.dtype == native.RESULT8_DT and np.array_equal(bits(r8["t"]), bits(exp["t"])) and np.array_equal(r8["bits"], want_bits)
+    small = g.trace(segs[:100], compact=True)
+    assert np.array_equal(small.view(np.uint32), r8[:100].view(np.uint32))
+    d_segs = torch.from_numpy(segs).cuda()
+    d8 = torch.zeros((len(segs), 2), dtype=torch.int32, device="cuda")
+    g.trace(d_segs, out=d8, compact=True)
+    assert np.array_equal(d8.cpu().numpy().view(np.uint32), r8.view(np.uint32).reshape(-1, 2))
+    # ordering: fill the segments on a side stream, trace on that stream without any synchronisation in between
+    side = torch.cuda.Stream()
+    big = torch.from_numpy(np.tile(segs, (8, 1))).cuda()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            work = torch.zeros_like(big)
+            for _ in range(4):
+                work.copy_(big * 0.5); work.add_(work)          # several kernels deep; ends up equal to `big`
+            out = torch.zeros((len(big), 4), dtype=torch.int32, device="cuda")
+            g.trace(work, out=out, async_=True)                 # api: current stream = side
+        side.synchronize()
+        got = out.cpu().numpy().view(native.RESULT_DT).reshape(-1)
+        _compare(got[: len(segs)], None, exp, None, "trace ordered after its producer")
+        _compare(got[-len(segs):], None, exp, None, "trace ordered after its producer (tail)")
+    g.close()
+
+
+def test_small_batches_and_latency_path(native, maps, oracle_mod):
+    """a batch of one (BSP::trace_seg) up to a few thousand segments takes the single-stream bounce-buffer path and
+    launches only as many CTAs as there is work for"""
+    m, _ = maps("rooms8")
+    segs = _segments(m, 3000, 500, 500, 90)
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    g = native.BspGpu(m)
+    for n in (1, 2, 33, 1000, 4096, 4097):
+        pos = np.zeros((n, 4), np.float32)
+        res = g.trace(segs[:n], out=np.zeros(n, native.RESULT_DT), pos=pos)
+        _compare(res, pos, exp[:n], exp_pos[:n], f"small batch {n}")
+        assert g.hit_count() == int((exp["flags"][:n] & 1).sum())
+        if n <= 4096:
+            assert g.info()["grid_ctas"] <= -(-n // 32)
+    g.close()
+
+
+def test_pageable_callers(native, maps, oracle_mod):
+    """plain (pageable) numpy arrays large enough to be page-locked for the call, with the option on and off"""
+    m, _ = maps("rooms8")
+    from tools import mapgen, seggen
+    lo, hi = mapgen.seg_bounds(m)
+    segs = seggen.uniform(31, 0, 1_500_000, lo, hi)                # 48 MB in, 24 MB out
+    exp, _, _ = oracle_mod.Port(m).trace(segs[:300_000])
+    g = native.BspGpu(m)
+    g.set_option(5, 200_000)
+    outs = []
+    for pageable in (1, 0):
+        g.set_option(17, pageable)
+        outs.append(g.trace(segs))
+        _compare(outs[-1][:300_000], None, exp, None, f"pageable option {pageable}")
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    g.close()
+
+
+def test_segment_binning(native, maps, oracle_mod):
+    """BSPGPU_OPT_BIN_SEGMENTS: the counting-sort pre-pass changes the order lanes pick segments up in,
+    never a result, and every result lands at its segment's own index"""
+    import torch
+    for name in ("city10k", "rooms8"):
+        m, _ = maps(name)
+        segs = _segments(m, 200_000, 200_000, 200_000, 8192)
+        exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+        g = native.BspGpu(m)
+        g.set_option(16, 1)
+        d_segs = torch.from_numpy(segs).cuda()
+        out = torch.zeros((len(segs), 4), dtype=torch.int32, device="cuda")
+        pos = torch.zeros((len(segs), 4), dtype=torch.float32, device="cuda")
+        for launch in (1 << 30, 100_000):
+            g.set_option(12, launch)
+            out.zero_(); pos.zero_()
+            g.trace(d_segs, out=out, pos=pos)
+            assert g.info()["last_prepass_ms"] > 0
+            _compare(out.cpu().numpy().view(native.RESULT_DT).reshape(-1), pos.cpu().numpy(), exp, exp_pos, f"{name} binned, launch cap {launch}")
+            assert g.hit_count() == int((exp["flags"] & 1).sum())
+        g.close()
+
+
+def test_clusters_and_pvs(native, maps, oracle_mod):
+    """batched position_to_leaf -> BSP_Leaf::cluster -> PVS bit (reference bsp_renderer.cc:147-168, bsp.h:129-134),
+    on the q3-style map that carries clusters and a real vis lump, loaded from its 17-slot file"""
+    from tools import mapgen, seggen
+    m, path = maps("q3style")
+    lo, hi = mapgen.seg_bounds(m)
+    pts = np.ascontiguousarray(seggen.uniform(9, 0, 100_000, lo, hi)[:, :3])
+    g = native.BspGpu(path)
+    nclusters = int(m.vis[:4].view(np.uint32)[0]); csize = int(m.vis[4:8].view(np.uint32)[0])
+    assert g.info()["num_clusters"] == nclusters > 8 and g.info()["num_leaves"] == len(m.leaves)
+    rows = m.vis[8:].reshape(nclusters, csize)
+    leaf_exp = oracle_mod.Port(m).leaf(np.ascontiguousarray(np.hstack((pts, np.zeros((len(pts), 1), np.float32)))))
+    cl_exp = m.leaves["cluster"][leaf_exp]
+    assert (cl_exp >= 0).any() and (cl_exp < 0).any()
+    for frm in (-1, 0, nclusters // 2, nclusters - 1):
+        leaf, cluster, vis = g.leaf_clusters(pts, from_cluster=frm, want_visible=True)
+        assert np.array_equal(leaf, leaf_exp) and np.array_equal(cluster, cl_exp)
+        if frm < 0:
+            want = np.ones(len(pts), np.uint8)
+        else:
+            c = np.maximum(cl_exp, 0)
+            want = ((rows[frm, c >> 3] >> (c & 7)) & 1).astype(np.uint8) * (cl_exp >= 0)
+        assert np.array_equal(vis, want), frm
+    # the renderer's loop: which leaves are drawn from a viewpoint
+    inside = pts[cl_exp >= 0][:20]
+    for p in inside:
+        vis, vc = g.visible_leaves(p)
+        assert vc >= 0
+        c = m.leaves["cluster"]
+        want = np.where(c >= 0, (rows[vc, np.maximum(c, 0) >> 3] >> (np.maximum(c, 0) & 7)) & 1, 0).astype(np.uint8)
+        assert np.array_equal(vis, want)
+    vis, vc = g.visible_leaves(pts[cl_exp < 0][0])
+    assert vc == -1 and vis.all()
+    with pytest.raises(native.BspGpuError):
+        g.leaf_clusters(pts[:4], from_cluster=nclusters, want_visible=True)
+    g.close()
+
+
 @pytest.mark.parametrize("mapname,kind,n", [("rooms8", "uniform", 64 * 1024 * 1024), ("city10k", "long", 128 * 1024 * 1024)])
 def test_full_size_properties(native, maps, oracle_mod, mapname, kind, n):
     """BASELINE.json sizes (C2: 64 Mi uniform segments on rooms8; C3: one GPU's 128 Mi-segment shard of the
@@ -188,11 +320,10 @@ def test_full_size_properties(native, maps, oracle_mod, mapname, kind, n):
         g.generate(segs, first, n, 0, 2, lo, hi)
     else:
         g.generate(segs, first, n, 1, 3, lo, hi, 0.25 * diag, diag)
-    fits_smem = g.info()["staged_bytes"] < 200 * 1024
-    configs = [(0, 0)] + ([(2, 0)] if fits_smem else []) + [(3, 0), (0, 1)]       # (variant, scheduler)
+    configs = [(0, -1), (3, -1), (3, 0), (0, 4)]       # (variant, shared-memory stack slots)
     ref_out, ref_hits = None, None
     for variant, sched in configs:
-        g.set_option(1, variant); g.set_option(9, sched)
+        g.set_option(1, variant); g.set_option(15, sched)
         out = torch.empty((n, 4), dtype=torch.int32, device="cuda")
         g.trace(segs, out=out)
         hits = g.hit_count()
@@ -207,7 +338,7 @@ def test_full_size_properties(native, maps, oracle_mod, mapname, kind, n):
             assert hits == ref_hits, (variant, sched)
             assert torch.equal(out, ref_out), (variant, sched)
             del out
-    stride = 4099
+    stride = 61                                      # >= 1 M rows of each configuration against the reference object
     idx = torch.arange(0, n, stride, device="cuda")
     sample = segs[idx].cpu().numpy()
     gi = first + np.arange(0, n, stride, dtype=np.uint64)
@@ -215,9 +346,16 @@ def test_full_size_properties(native, maps, oracle_mod, mapname, kind, n):
     want = np.vstack([seggen.uniform(2, int(i), 1, lo, hi) if kind == "uniform" else seggen.long_rays(3, int(i), 1, lo, hi, 0.25 * diag, diag)
                       for i in gi[:64]])
     assert np.array_equal(bits(sample[:64]), bits(want))
-    exp, _, _ = oracle_mod.Port(m).trace(sample)
+    assert len(sample) >= 1_000_000
     got = ref_out[idx].cpu().numpy().view(native.RESULT_DT).reshape(-1)
-    _compare(got, None, exp, None, f"{mapname} {n} strided sample")
+    if oracle_mod.have_reference():
+        # the unmodified reference (work_queue-threaded): {hit, t} are its outputs
+        ref = oracle_mod.Reference(maps(mapname)[1])
+        r = ref.trace(sample, threads=max(1, len(__import__("os").sched_getaffinity(0))))
+        bad = ((got["flags"] & 1).astype(np.uint8) != r["hit"]) | (bits(got["t"]) != bits(r["t"]))
+        assert not bad.any(), f"{mapname} {n}: {int(bad.sum())} of {len(sample)} sampled rows differ from the reference; first {int(np.nonzero(bad)[0][0])}"
+    exp, _, _ = oracle_mod.Port(m).trace(sample[:200_000])
+    _compare(got[:200_000], None, exp, None, f"{mapname} {n} strided sample (extension fields vs port)")
     g.close()
 
 
@@ -284,16 +422,20 @@ def test_golden_reference_outputs_for_extreme_floats(native, name):
     g.close()
 
 
-@pytest.mark.parametrize("mapname", ["city10k", "tilted"])
-def test_both_schedulers_agree(native, maps, oracle_mod, mapname):
-    m, _ = maps(mapname)
-    segs = _segments(m, 100_000, 200_000, 50_000, 4096)
-    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+def test_experiment_options_are_rejected_in_the_product_build(native, maps):
+    """the measured-slower round-1 kernels are not in libbspgpu.so (only in -DBSPGPU_EXPERIMENTS builds): asking for
+    them fails loudly instead of silently running something else; so do values that could hang a kernel."""
+    m, _ = maps("kat1")
     g = native.BspGpu(m)
-    for sched in (0, 1, 2, 4):
-        g.set_option(9, sched)
-        res = g.trace(segs)
-        _compare(res, None, exp, exp_pos, f"scheduler {sched}")
+    for opt, val in ((9, 1), (9, 3), (14, 1), (8, -5), (8, 7), (8, 1 << 40), (6, 0), (6, 33), (11, 0), (10, 0), (5, 10), (15, 9)):
+        with pytest.raises(native.BspGpuError):
+            g.set_option(opt, val)
+    g.set_option(8, 0)                               # 0 = default
+    g.set_option(1, 2)                               # TOPTREE is accepted as a value but needs an experiments build to run
+    with pytest.raises(native.BspGpuError, match="EXPERIMENTS"):
+        g.trace(np.zeros((4, 8), np.float32))
+    g.set_option(1, 0)
+    assert len(g.trace(np.ones((4, 8), np.float32))) == 4
     g.close()
 
 
@@ -307,7 +449,7 @@ def test_odd_map_on_gpu(native, oracle_mod):
     segs[:1000, 0:3] = np.round(segs[:1000, 0:3] / 16) * 16
     exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
     g = native.BspGpu(m)
-    for variant in (1, 2, 3):
+    for variant in (1, 3):
         g.set_option(1, variant)
         pos = np.zeros((len(segs), 4), np.float32)
         res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
@@ -315,7 +457,7 @@ def test_odd_map_on_gpu(native, oracle_mod):
     g.close()
 
 
-@pytest.mark.parametrize("variant", ["toptree", "global"])
+@pytest.mark.parametrize("variant", ["global"])
 def test_parity_mega200k_short_moves(native, maps, oracle_mod, variant):
     """C5: ~200k-brush map (54 MB flattened image, L2-resident), short player-movement segments."""
     from tools import mapgen, seggen
@@ -363,26 +505,6 @@ def test_depth_frame_demo(native, maps, oracle_mod):
         exp, _, _ = oracle_mod.Port(m).trace(seggen.camera(views, w, h, w * h, w * h))
         assert np.array_equal(bits(t.reshape(-1)), bits(exp["t"]))
         assert np.array_equal(hit.reshape(-1), (exp["flags"] & 1).astype(bool))
-    g.close()
-
-
-@pytest.mark.parametrize("mapname,variant", [("rooms8", 1), ("rooms8", 3), ("city10k", 3), ("kat1", 1), ("tilted", 1)])
-def test_two_segment_scheduler(native, maps, oracle_mod, mapname, variant):
-    """BSPGPU_OPT_SCHEDULER=3: every lane owns two segments (one parked in shared memory)."""
-    m, _ = maps(mapname)
-    segs = _segments(m, 200_000, 150_000, 50_000, 8192)
-    exp, exp_pos, ctr = oracle_mod.Port(m).trace(segs)
-    g = native.BspGpu(m)
-    g.set_option(9, 3); g.set_option(1, variant)
-    for threads, refill, steps, side, thr in ((0, 8, 0, 8, 16), (128, 1, 1, 1, 1), (512, 32, 1000, 1000, 32)):
-        g.set_option(2, threads); g.set_option(6, refill); g.set_option(7, steps); g.set_option(10, side); g.set_option(11, thr)
-        pos = np.zeros((len(segs), 4), np.float32)
-        res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
-        _compare(res, pos, exp, exp_pos, f"dual {mapname} v{variant} {threads}/{refill}/{steps}/{side}/{thr}")
-        assert g.hit_count() == ctr["hits"]
-    for n in (1, 31, 33, 65, 1000):
-        res = g.trace(segs[:n])
-        _compare(res, None, exp[:n], None, f"dual n={n}")
     g.close()
 
 
@@ -450,7 +572,7 @@ def test_start_grid(native, maps, oracle_mod, name):
     exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
     g = native.BspGpu(m)
     assert g.info()["start_grid_cells"] > 100_000
-    for variant in ((1, 3) if g.info()["staged_bytes"] < 200 * 1024 else (3, 2)):
+    for variant in ((1, 3) if g.info()["staged_bytes"] < 200 * 1024 else (3,)):
         g.set_option(1, variant)
         for grid in (1, 0):
             g.set_option(13, grid)
@@ -460,26 +582,38 @@ def test_start_grid(native, maps, oracle_mod, name):
     g.close()
 
 
-@pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k", "tilted", "mega200k"])
-def test_packed_nodes(native, maps, oracle_mod, name):
-    """BSPGPU_OPT_PACKED_NODES: the GLOBAL variant's two-level node records give the same bits as one record per node,
-    with and without the start grid and under small phase budgets (a two-level step may suspend between records only)."""
-    from helpers import grid_adversarial_segments
+@pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k", "tilted"])
+def test_axis_node_records(native, maps, oracle_mod, name):
+    """node planes with a bitwise +unit normal are stored as their axis and plain rays skip the dot products
+    (map_layout.h: NodeRec, trace_core.h: ray_is_plain); rays with zero / non-finite components are traced by the
+    lane that draws them with the general arithmetic.  Same bits as an image flattened with general planes only,
+    as the oracle, in both staging variants, with and without the start grid."""
+    from helpers import extreme_segments, grid_adversarial_segments
     from tools import mapgen, seggen
     m, _ = maps(name)
     lo, hi = mapgen.seg_bounds(m)
-    segs = np.vstack((_segments(m, 50_000, 30_000, 150_000, 4096), seggen.long_rays(79, 0, 200_000, lo, hi, 0.01, 8.0)))
+    segs = np.vstack((_segments(m, 50_000, 30_000, 150_000, 4096), seggen.long_rays(79, 0, 200_000, lo, hi, 0.01, 8.0),
+                      extreme_segments(40_000, float(np.abs(np.concatenate((lo, hi))).max()))))
+    # a sprinkling of exact zeros (both signs) in otherwise ordinary segments
+    rs = np.random.Generator(np.random.PCG64(3))
+    z = rs.integers(0, len(segs), 60_000)
+    segs[z, rs.integers(0, 3, len(z))] = np.array([0.0, -0.0], np.float32)[rs.integers(0, 2, len(z))]
     g = native.BspGpu(m)
     if g.info()["start_grid_cells"]:
         segs = np.vstack((segs, grid_adversarial_segments(m, 200_000)))
-    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
-    g.set_option(1, 3)
-    for packed, grid, steps in ((1, 1, 8), (1, 0, 1), (0, 1, 8), (1, -1, 3)):
-        g.set_option(14, packed); g.set_option(13, grid); g.set_option(7, steps)
-        pos = np.zeros((len(segs), 4), np.float32)
-        res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
-        _compare(res, pos, exp, exp_pos, f"{name} packed {packed} grid {grid} steps {steps}")
-    g.close()
+    with np.errstate(all="ignore"):
+        exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
+    gg = native.BspGpu(m, general_planes_only=True)
+    assert gg.info()["num_general_planes"] == gg.info()["num_nodes"]
+    if name in ("rooms8", "city10k"):
+        assert g.info()["num_general_planes"] == 0
+    for h, what in ((g, "axis records"), (gg, "general planes only")):
+        for variant in ((1, 3) if h.info()["staged_bytes"] < 200 * 1024 else (3,)):
+            for grid, steps in ((1, 8), (0, 1)):
+                h.set_option(1, variant); h.set_option(13, grid); h.set_option(7, steps)
+                res = h.trace(segs)
+                _compare(res, None, exp, None, f"{name} {what} variant {variant} grid {grid} steps {steps}")
+    g.close(); gg.close()
 
 
 @pytest.mark.parametrize("name", ["kat1", "rooms8", "city10k", "tilted", "mega200k"])
@@ -497,7 +631,7 @@ def test_smem_stack(native, maps, oracle_mod, name):
         g.set_option(15, slots); g.set_option(7, steps)
         pos = np.zeros((len(segs), 4), np.float32)
         res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
-        assert g.info()["smem_bytes"] == slots * 256 * 16
+        assert g.info()["smem_bytes"] == slots * 256 * 16 and g.info()["smem_stack_slots"] == slots
         _compare(res, pos, exp, exp_pos, f"{name} smem stack {slots} steps {steps}")
     if g.info()["staged_bytes"] < 140 * 1024:
         # the same behind a staged map (SMEM variant, one 1024-thread CTA per SM); explicit request only

@@ -49,6 +49,7 @@ class IBSP:
     brushes: np.ndarray
     brush_sides: np.ndarray
     meta: dict = dataclasses.field(default_factory=dict)
+    vis: np.ndarray = None   # the raw visibility lump (uint8): {u32 num_clusters, u32 cluster_size, pvs rows}, reference bsp.h:129-134
 
     def counts(self) -> dict:
         return {k: int(len(getattr(self, k))) for k in
@@ -68,7 +69,8 @@ def to_bytes(m: IBSP, num_lumps: int = NUM_LUMPS) -> bytes:
         LUMP_LEAFBRUSHES: np.ascontiguousarray(m.leaf_brushes, LEAFBRUSH_DT).tobytes(),
         LUMP_BRUSHES: np.ascontiguousarray(m.brushes, BRUSH_DT).tobytes(),
         LUMP_BRUSHSIDES: np.ascontiguousarray(m.brush_sides, BRUSHSIDE_DT).tobytes(),
-        LUMP_VISIBILITY: np.zeros(2, "<u4").tobytes(),  # {num_clusters=0, cluster_size=0}
+        # {num_clusters=0, cluster_size=0} unless the map carries clusters
+        LUMP_VISIBILITY: np.zeros(2, "<u4").tobytes() if m.vis is None else np.ascontiguousarray(m.vis, np.uint8).tobytes(),
     }
     header_bytes = 8 + 8 * num_lumps
     dirent = np.zeros((num_lumps, 2), "<u4")
@@ -109,6 +111,7 @@ def from_bytes(blob: bytes) -> IBSP:
         leaf_brushes=lump(LUMP_LEAFBRUSHES, LEAFBRUSH_DT), brushes=lump(LUMP_BRUSHES, BRUSH_DT),
         brush_sides=lump(LUMP_BRUSHSIDES, BRUSHSIDE_DT),
         meta={"magic": blob[:4], "version": int(np.frombuffer(blob, "<u4", 1, 4)[0])},
+        vis=lump(LUMP_VISIBILITY, np.dtype("u1")),
     )
 
 

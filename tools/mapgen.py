@@ -680,7 +680,12 @@ def tilted(seed: int = 9, n_brushes: int = 260, leaf_max: int = 1, max_depth: in
                      np.concatenate(leaves).astype(np.uint32), brush_arr, side_arr, meta)
 
 
-MAPS = {"kat0": kat0, "kat1": kat1, "rooms8": rooms8, "city10k": city10k, "mega200k": mega200k, "tilted": tilted}
+def q3style(seed: int = 12) -> ibsp.IBSP:
+    from tools import mapgen_q3
+    return mapgen_q3.q3style(seed)
+
+
+MAPS = {"kat0": kat0, "kat1": kat1, "rooms8": rooms8, "city10k": city10k, "mega200k": mega200k, "tilted": tilted, "q3style": q3style}
 
 
 def cache_dir() -> str:
@@ -691,7 +696,8 @@ def cache_dir() -> str:
 
 def _source_digest() -> str:
     h = hashlib.sha256()
-    for fn in (__file__, ibsp.__file__, os.path.join(os.path.dirname(os.path.abspath(__file__)), "bspc.c")):
+    here = os.path.dirname(os.path.abspath(__file__))
+    for fn in (__file__, ibsp.__file__, os.path.join(here, "bspc.c"), os.path.join(here, "mapgen_q3.py")):
         with open(fn, "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:12]
@@ -706,7 +712,13 @@ def get_map(name: str, use_cache: bool = True):
         m.meta.update(np.load(metap, allow_pickle=True).item())
         return m, path
     m = MAPS[name]()
-    ibsp.write(m, path + ".tmp%d" % os.getpid())
+    for old in os.listdir(cache_dir()):           # files of earlier source revisions
+        if old.startswith(name + "-") and not old.startswith(os.path.basename(path)):
+            try:
+                os.remove(os.path.join(cache_dir(), old))
+            except OSError:
+                pass
+    ibsp.write(m, path + ".tmp%d" % os.getpid(), num_lumps=int(m.meta.get("num_lumps", ibsp.NUM_LUMPS)))
     os.replace(path + ".tmp%d" % os.getpid(), path)
     np.save(metap + ".tmp%d.npy" % os.getpid(), np.array(m.meta, dtype=object), allow_pickle=True)
     os.replace(metap + ".tmp%d.npy" % os.getpid(), metap)
