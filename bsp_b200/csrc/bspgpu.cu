@@ -75,43 +75,44 @@ int effective_slots( int mode, int threads, int64_t want ) {
 	const int s = want <= 2 ? 2 : ( want <= 4 ? 4 : ( want <= 6 ? 6 : 8 ) );
 	return threads > 256 && s > 6 ? 6 : s;
 }
-template< int M, int S, int T, int B >
+template< int M, int S, int T, int B, bool G >
 TraceKernel pick_slots( int slots ) {
 	if constexpr( ( M == kGlobal && T == 256 ) || ( M == kSmemAll && T == 1024 ) ) {
 		switch( slots ) {
-			case 0: return trace_phased< M, S, T, B, 0 >;
-			case 2: return trace_phased< M, S, T, B, 2 >;
-			case 4: return trace_phased< M, S, T, B, 4 >;
-			case 6: return trace_phased< M, S, T, B, 6 >;
+			case 0: return trace_phased< M, S, T, B, 0, G >;
+			case 2: return trace_phased< M, S, T, B, 2, G >;
+			case 4: return trace_phased< M, S, T, B, 4, G >;
+			case 6: return trace_phased< M, S, T, B, 6, G >;
 			default:
-				if constexpr( T == 256 ) return trace_phased< M, S, T, B, 8 >;
-				else return trace_phased< M, S, T, B, 6 >;
+				if constexpr( T == 256 ) return trace_phased< M, S, T, B, 8, G >;
+				else return trace_phased< M, S, T, B, 6, G >;
 		}
 	}
-	else return slots ? trace_phased< M, S, T, B, 6 > : trace_phased< M, S, T, B, 0 >;
+	else return slots ? trace_phased< M, S, T, B, 6, G > : trace_phased< M, S, T, B, 0, G >;
 }
-template< int M, int S >
+template< int M, int S, bool G >
 TraceKernel pick_threads( int threads, int slots ) {
-	if( threads <= 256 ) return pick_slots< M, S, 256, M == kGlobal ? 5 : 1 >( slots );
-	if( threads <= 512 ) return pick_slots< M, S, 512, 1 >( slots );
-	return pick_slots< M, S, 1024, 1 >( slots );
+	if( threads <= 256 ) return pick_slots< M, S, 256, M == kGlobal ? 5 : 1, G >( slots );
+	if( threads <= 512 ) return pick_slots< M, S, 512, 1, G >( slots );
+	return pick_slots< M, S, 1024, 1, G >( slots );
 }
+/* depth <= 32: 32-entry local overflow stack; anything deeper (up to the 128 levels bspgpu_create accepts): 128 entries */
 template< int M >
-TraceKernel pick_stack( int depth, int threads, int slots ) {
-	if( depth <= 32 ) return pick_threads< M, 32 >( threads, slots );
-	if( depth <= 64 ) return pick_threads< M, 64 >( threads, slots );
-	return pick_threads< M, 128 >( threads, slots );
+TraceKernel pick_stack( int depth, int threads, int slots, bool general ) {
+	if( depth <= 32 ) return general ? pick_threads< M, 32, true >( threads, slots ) : pick_threads< M, 32, false >( threads, slots );
+	return general ? pick_threads< M, 128, true >( threads, slots ) : pick_threads< M, 128, false >( threads, slots );
 }
-TraceKernel pick_kernel( int mode, int depth, int threads, int sched, int slots ) {
+/* general: the map has node planes that are not axis records */
+TraceKernel pick_kernel( int mode, int depth, int threads, int sched, int slots, bool general ) {
 #ifdef BSPGPU_EXPERIMENTS
 	if( sched == 4 ) {
 		if( depth <= 32 ) return threads <= 256 ? trace_simple< kGlobal, 32, 256 > : trace_simple< kGlobal, 32, 1024 >;
 		return threads <= 256 ? trace_simple< kGlobal, 128, 256 > : trace_simple< kGlobal, 128, 1024 >;
 	}
-	if( mode == kSmemTop ) return pick_stack< kSmemTop >( depth, threads, slots );
+	if( mode == kSmemTop ) return pick_stack< kSmemTop >( depth, threads, slots, general );
 #endif
 	( void ) sched;
-	return mode == kSmemAll ? pick_stack< kSmemAll >( depth, threads, slots ) : pick_stack< kGlobal >( depth, threads, slots );
+	return mode == kSmemAll ? pick_stack< kSmemAll >( depth, threads, slots, general ) : pick_stack< kGlobal >( depth, threads, slots, general );
 }
 
 } // namespace
@@ -171,7 +172,7 @@ int configure( bspgpu * h ) {
 			slots = full_slot_range( mode, threads ) ? slots - 2 : 0;
 		smem += ( uint32_t ) slots * ( uint32_t ) threads * 16u;
 	}
-	TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched, slots );
+	TraceKernel kernel = pick_kernel( mode, ( int ) h->lay.tree_depth, threads, ( int ) h->opt_sched, slots, h->lay.num_gplanes > 0 );
 	CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );
 	int ctas = ( int ) h->opt_ctas;
 	int occ = 0;
@@ -202,6 +203,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 	p.side_steps = ( uint32_t ) h->opt_side_steps;
 	p.leaf_threshold = ( uint32_t ) h->opt_leaf_threshold;
 	p.hits = h->d_counters;
+	p.exotic_list = h->d_exotic;
 	p.grid.d = h->lay.grid;
 	const bool use_grid = h->opt_start_grid < 0 ? mode != kSmemAll : h->opt_start_grid != 0;
 	p.grid.cells = ( use_grid && h->lay.grid.dim[ 0 ] ) ? reinterpret_cast< const int32_t * >( h->d_image + h->lay.off_grid ) : nullptr;
@@ -218,8 +220,8 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 		uint64_t grid = ( cnt + ( uint64_t ) block_segs * warps_per_cta - 1 ) / ( ( uint64_t ) block_segs * warps_per_cta );
 		if( grid > ( uint64_t ) h->cfg_grid ) grid = ( uint64_t ) h->cfg_grid;
 		if( h->opt_sched == 4 ) grid = ( uint64_t ) h->cfg_grid;
-		unsigned long long * next = h->d_counters + 1 + ( h->launch_seq++ % kCounterSlots );
-		CK( cudaMemsetAsync( next, 0, sizeof( unsigned long long ), st ) );
+		unsigned long long * next = h->d_counters + 2 + 2 * ( h->launch_seq++ % kCounterSlots );   /* {work counter, exotic-ray count} */
+		CK( cudaMemsetAsync( next, 0, 2 * sizeof( unsigned long long ), st ) );
 		p.block_segs = block_segs;
 		p.perm = d_perm ? d_perm + done : nullptr;
 		/* with a permutation every slot names an absolute segment index, so the arrays are not advanced */
@@ -232,9 +234,14 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 		p.n = ( uint32_t ) cnt;
 		p.next = next;
 		kernel<<< ( unsigned ) grid, threads, smem, st >>>( p );
+		/* rays the axis shortcut does not cover (zero start coordinate, non-finite component): counted by the kernel above, traced
+		 * here; returns immediately when there were none */
+		uint64_t xgrid = ( cnt + 255 ) / 256;
+		if( xgrid > ( uint64_t ) h->sm_count * 8 ) xgrid = ( uint64_t ) h->sm_count * 8;
+		trace_exotic_kernel<<< ( unsigned ) xgrid, 256, 0, st >>>( p );
 		CK( cudaGetLastError() );
 		h->last_grid = ( uint32_t ) grid;
-		h->last_launches++;
+		h->last_launches += 2;
 	}
 	return BSPGPU_OK;
 }
@@ -529,8 +536,9 @@ int bspgpu_create_opts( bspgpu_t ** out, const bspgpu_map_desc * lumps, int devi
 		if( e != cudaSuccess ) break;
 		if( ( e = cudaMalloc( &h->d_image, flat.layout.total_bytes ) ) != cudaSuccess ) break;
 		if( ( e = cudaMemcpy( h->d_image, flat.image.data(), flat.layout.total_bytes, cudaMemcpyHostToDevice ) ) != cudaSuccess ) break;
-		if( ( e = cudaMalloc( &h->d_counters, ( 1 + kCounterSlots ) * sizeof( unsigned long long ) ) ) != cudaSuccess ) break;
-		if( ( e = cudaMemset( h->d_counters, 0, ( 1 + kCounterSlots ) * sizeof( unsigned long long ) ) ) != cudaSuccess ) break;
+		if( ( e = cudaMalloc( &h->d_counters, ( 2 + 2 * kCounterSlots ) * sizeof( unsigned long long ) ) ) != cudaSuccess ) break;
+		if( ( e = cudaMemset( h->d_counters, 0, ( 2 + 2 * kCounterSlots ) * sizeof( unsigned long long ) ) ) != cudaSuccess ) break;
+		if( ( e = cudaMalloc( &h->d_exotic, kExoticCap * sizeof( uint32_t ) ) ) != cudaSuccess ) break;
 		if( ( e = cudaMallocHost( ( void ** ) &h->h_small, kSmallCall * 64 ) ) != cudaSuccess ) break;
 	} while( 0 );
 	if( e != cudaSuccess ) {
@@ -589,6 +597,7 @@ void bspgpu_destroy( bspgpu_t * h ) {
 	bspgpu_dist_release( h );
 	if( h->d_image ) cudaFree( h->d_image );
 	if( h->d_counters ) cudaFree( h->d_counters );
+	if( h->d_exotic ) cudaFree( h->d_exotic );
 	if( h->d_vis ) cudaFree( h->d_vis );
 	if( h->d_scratch ) cudaFree( h->d_scratch );
 	if( h->h_small ) cudaFreeHost( h->h_small );

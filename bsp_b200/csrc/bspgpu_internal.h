@@ -46,7 +46,8 @@ struct bspgpu {
 	cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
 	unsigned char * d_image = nullptr;
 	bspk::MapImageLayout lay;
-	unsigned long long * d_counters = nullptr;   /* [0] hits, [1 .. kCounterSlots] work counters */
+	unsigned long long * d_counters = nullptr;   /* [0] hits, then per in-flight launch a pair {work counter, exotic-ray count} */
+	uint32_t * d_exotic = nullptr;               /* indices of the rays the follow-up kernel traces (trace_kernels.cuh: kExoticCap entries) */
 	uint32_t launch_seq = 0;
 
 	/* visibility lump (bspgpu_set_vis) */

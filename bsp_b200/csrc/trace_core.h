@@ -105,7 +105,9 @@ BSPK_HD void node_plane_exact( const Map & map, int32_t i, float & nx, float & n
 BSPK_HD bool ray_is_plain( const Ray & r ) {
 	const float p = ( r.sx * r.sy ) * r.sz;   /* finite and non-zero => every start component is finite and non-zero */
 	const float q = ( r.dx * r.dy ) * r.dz;   /* finite => every direction component is finite (inf * 0 = NaN) */
-	return fabsf( p ) > 0.0f && fabsf( p ) < INFINITY && fabsf( q ) < INFINITY;
+	/* x * 0 is 0 for finite x and NaN for an infinite or NaN x: one multiply-add and one compare test both products
+	 * (products that overflow or underflow send a plain ray down the general path: slower, never wrong) */
+	return p != 0.0f && ( p * 0.0f + q * 0.0f ) == 0.0f;
 }
 
 /* trace_seg_tree from `node` down to a leaf reference; pending far sides go on the stack. */
@@ -381,16 +383,29 @@ BSPK_HD void lane_node_apply( Lane & l, const Stack & stack, float denom, float 
 	}
 }
 
+/* component `w` (0, 1, 2) of the ray's start and direction.  On the device this is spelled as predicated selects: written as
+ * `w == 0 ? x : w == 1 ? y : z` the compiler turns it into an INDEXED load and moves the whole ray to local memory (two LDL per
+ * node step and the lane state spilled around it: measured -19 % on long rays). */
+BSPK_HD void ray_axis( const Ray & r, uint32_t w, float & s, float & d ) {
+#ifdef __CUDA_ARCH__
+	asm( "{\n\t.reg .pred p0, p1;\n\tsetp.eq.u32 p0, %2, 0;\n\tsetp.eq.u32 p1, %2, 1;\n\t"
+	     "selp.f32 %0, %4, %5, p1;\n\tselp.f32 %0, %3, %0, p0;\n\tselp.f32 %1, %7, %8, p1;\n\tselp.f32 %1, %6, %1, p0;\n\t}"
+	     : "=&f"( s ), "=&f"( d ) : "r"( w ), "f"( r.sx ), "f"( r.sy ), "f"( r.sz ), "f"( r.dx ), "f"( r.dy ), "f"( r.dz ) );
+#else
+	s = w == 0u ? r.sx : ( w == 1u ? r.sy : r.sz );
+	d = w == 0u ? r.dx : ( w == 1u ? r.dy : r.dz );
+#endif
+}
+
 /* the lane's ray must be plain (ray_is_plain) */
 template< class Map, class Stack >
 BSPK_HD void lane_node_step( const Map & map, Lane & l, const Stack & stack ) {
 	float d; int32_t c0, c1; uint32_t w;
 	map.node( l.cur, d, c0, c1, w );
 	float denom, sdot;
-	if( w < kGeneralPlane ) {
-		sdot = w == 0u ? l.r.sx : ( w == 1u ? l.r.sy : l.r.sz );                   /* = dot( start, e_w ), :221 */
-		denom = w == 0u ? l.r.dx : ( w == 1u ? l.r.dy : l.r.dz );                  /* = dot( e_w, dir ),   :220 */
-	}
+	/* Map::kGeneralPlanes == false: the map has no node plane other than +unit normals (every kd-style map), and the general
+	 * path is not even compiled in -- left in, the compiler predicates it into every step (+18 instructions of 67) */
+	if( !Map::kGeneralPlanes || w < kGeneralPlane ) ray_axis( l.r, w, sdot, denom );   /* = dot( start, e_w ) :221, dot( e_w, dir ) :220 */
 	else {
 		float nx, ny, nz;
 		map.gplane( w - kGeneralPlane, nx, ny, nz );
@@ -555,6 +570,7 @@ BSPK_HD void make_pos( const Ray & r, const HitState & h, float & px, float & py
 
 /* plain-pointer accessor over the flattened image (global memory on the device, host memory in hostsim) */
 struct ImageMap {
+	static const bool kGeneralPlanes = true;
 	const NodeRec * nodes;
 	const PlaneRec * gplanes;
 	const BrushRef * refs;

@@ -22,7 +22,8 @@
  * N4  bin_* kernels: optional counting sort of the segments by start-grid cell (a coherence pre-pass).
  *
  * Rays with a zero start coordinate or a non-finite component do not take the axis shortcut (trace_core.h:
- * ray_is_plain); the lane that draws one traces it on the spot with the general arithmetic (trace_exotic).
+ * ray_is_plain); the lane that draws one only counts it, and trace_exotic_kernel -- launched behind every trace
+ * kernel, a no-op when the count is zero -- traces such rays with the general arithmetic.
  *
  * No tensor cores: the walk is a dependent chain of 16/32-byte gathers and a handful of fp32
  * ops per node/side, not a contraction.
@@ -41,6 +42,7 @@
 namespace bspk {
 
 enum Mode { kSmemAll = 0, kSmemTop = 1, kGlobal = 2 };
+static const uint32_t kExoticCap = 1u << 16;
 
 struct TraceParams {
 	const unsigned char * image;      /* flattened map in global memory */
@@ -60,7 +62,8 @@ struct TraceParams {
 	uint32_t side_steps;              /* side steps per lane per leaf phase */
 	uint32_t leaf_threshold;          /* lanes waiting in a leaf that make the warp run a leaf phase */
 	StartGrid grid;                   /* cells == null: every walk starts at node 0 */
-	unsigned long long * next;        /* work counter, zeroed before launch */
+	unsigned long long * next;        /* work counter, zeroed before launch; next[1] counts the segments left to trace_exotic_kernel */
+	uint32_t * exotic_list;           /* the first kExoticCap of those segments' indices (beyond that the follow-up kernel rescans the launch) */
 	unsigned long long * hits;        /* accumulated hit count */
 };
 
@@ -141,6 +144,7 @@ __device__ __forceinline__ uint32_t opaque_u32( uint32_t v ) {
 }
 
 struct SmemAllMap {
+	static const bool kGeneralPlanes = true;
 	uint32_t nodes, gplanes, refs, sides_even, sides_odd;   /* shared-window byte addresses of the sections */
 	__device__ __forceinline__ void node( int32_t i, float & d, int32_t & c0, int32_t & c1, uint32_t & w ) const {
 		const uint4 r = lds128u( nodes + ( ( uint32_t ) i << 4 ) );
@@ -168,6 +172,7 @@ __device__ __forceinline__ void ldg_side_pair( const SideRec * p, float & n0x, f
 }
 
 struct GlobalMap {
+	static const bool kGeneralPlanes = true;
 	const NodeRec * nodes; const PlaneRec * gplanes; const BrushRef * refs; const SideRec * side_pairs;   /* global memory, read-only path */
 	const NodeOrig * node_orig;
 	__device__ __forceinline__ void node( int32_t i, float & d, int32_t & c0, int32_t & c1, uint32_t & w ) const {
@@ -202,6 +207,7 @@ __device__ __forceinline__ void bind_global( const TraceParams & p, GlobalMap & 
 
 #ifdef BSPGPU_EXPERIMENTS
 struct SmemTopMap {
+	static const bool kGeneralPlanes = true;
 	uint32_t top;          /* shared-window byte address of nodes [0, top_nodes) */
 	uint32_t top_nodes;
 	GlobalMap g;
@@ -220,17 +226,19 @@ struct SmemTopMap {
 };
 #endif
 
-template< int kMode > struct MapOf;
-template<> struct MapOf< kSmemAll > { typedef SmemAllMap type; };
-template<> struct MapOf< kGlobal > { typedef GlobalMap type; };
+/* kGeneral = false: the accessor of a map all of whose node planes are axis records (trace_core.h: lane_node_step) */
+template< class Base, bool kGeneral > struct PlaneKinds : Base { static const bool kGeneralPlanes = kGeneral; };
+template< int kMode, bool kGeneral > struct MapOf;
+template< bool kGeneral > struct MapOf< kSmemAll, kGeneral > { typedef PlaneKinds< SmemAllMap, kGeneral > type; };
+template< bool kGeneral > struct MapOf< kGlobal, kGeneral > { typedef PlaneKinds< GlobalMap, kGeneral > type; };
 #ifdef BSPGPU_EXPERIMENTS
-template<> struct MapOf< kSmemTop > { typedef SmemTopMap type; };
+template< bool kGeneral > struct MapOf< kSmemTop, kGeneral > { typedef PlaneKinds< SmemTopMap, kGeneral > type; };
 #endif
 
 /* Stage what this mode keeps in shared memory -- one thread issues TMA bulk copies (cp.async.bulk, 32 KB each),
  * everyone waits on the mbarrier's transaction count -- and bind the map accessor to shared / global memory. */
-template< int kMode >
-__device__ __forceinline__ void stage_and_bind( const TraceParams & p, unsigned char * smem, uint64_t * stage_bar, typename MapOf< kMode >::type & map ) {
+template< int kMode, class Map >
+__device__ __forceinline__ void stage_and_bind( const TraceParams & p, unsigned char * smem, uint64_t * stage_bar, Map & map ) {
 	if( ( kMode == kSmemAll || kMode == kSmemTop ) && p.staged_bytes > 0 ) {
 		if( threadIdx.x == 0 ) {
 			mbar_init( stage_bar, 1 );
@@ -294,19 +302,11 @@ __device__ __forceinline__ void store_result( const TraceParams & p, uint32_t se
 	}
 }
 
-/* A ray that is not plain (trace_core.h: ray_is_plain -- a zero start coordinate, an infinite or NaN component) is
- * traced here start to finish with the general arithmetic over the image in global memory: rare, so it is kept out
- * of line and out of the hot loop's register budget. */
-__device__ __noinline__ void trace_exotic( const TraceParams & p, float sx, float sy, float sz, float dx, float dy, float dz, HitState & h ) {
-	GlobalMap g;
-	bind_global( p, g );
-	Ray r; r.sx = sx; r.sy = sy; r.sz = sz; r.dx = dx; r.dy = dy; r.dz = dz;
-	trace_one< GlobalMap, 128 >( g, r, h );
-}
-
 /* read segment `sidx` and begin its walk: at node 0 (bsp.cc:263) or at the start-grid reference of its cell.
- * Returns false when the segment was not plain and has been traced (and stored) on the spot; the lane stays idle. */
-__device__ __forceinline__ bool lane_load_segment( const TraceParams & p, uint32_t sidx, Lane & l, const uint32_t * side_plane, uint32_t & my_hits ) {
+ * A ray that is not plain (trace_core.h: ray_is_plain -- a zero start coordinate, an infinite or NaN component) cannot take
+ * the axis shortcut: it is only counted here (next[1]) and left to trace_exotic_kernel, which runs right behind this kernel
+ * and traces such rays start to finish with the general arithmetic.  Returns false for them; the lane stays idle. */
+__device__ __forceinline__ bool lane_load_segment( const TraceParams & p, uint32_t sidx, Lane & l ) {
 	float sx, sy, sz, ex, ey, ez;
 	load_endpoints( p, sidx, sx, sy, sz, ex, ey, ez );
 	/* the start reference first, the lane set-up once after it (one copy of the initialisation instead of one per grid outcome) */
@@ -314,10 +314,8 @@ __device__ __forceinline__ bool lane_load_segment( const TraceParams & p, uint32
 	lane_start( l, sx, sy, sz, ex, ey, ez );
 	lane_start_at( l, ref );
 	if( !ray_is_plain( l.r ) ) {
-		HitState h;
-		trace_exotic( p, l.r.sx, l.r.sy, l.r.sz, l.r.dx, l.r.dy, l.r.dz, h );
-		store_result( p, sidx, l.r, h, side_plane );
-		my_hits += ( uint32_t ) h.hit;
+		const unsigned long long k = atomicAdd( p.next + 1, 1ull );
+		if( k < kExoticCap ) p.exotic_list[ k ] = sidx;
 		l.cur = kCurIdle;
 		return false;
 	}
@@ -372,12 +370,12 @@ __device__ __forceinline__ void stack_get( const SmemStack< kSlots, kStride > & 
  * a leaf phase when at least `leaf_threshold` lanes wait in a leaf (or nobody can step nodes),
  * otherwise a node phase.  Lanes of the other kind just keep their registers.  Finished lanes
  * are re-filled as before. */
-template< int kMode, int kStack, int kMaxThreads, int kMinBlocks, int kSmemSlots = 0 >
+template< int kMode, int kStack, int kMaxThreads, int kMinBlocks, int kSmemSlots, bool kGeneral >
 __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const __grid_constant__ TraceParams p ) {
 	extern __shared__ __align__( 128 ) unsigned char smem[];
 	__shared__ __align__( 8 ) uint64_t stage_bar;
 
-	typename MapOf< kMode >::type map;
+	typename MapOf< kMode, kGeneral >::type map;
 	stage_and_bind< kMode >( p, smem, &stage_bar, map );
 	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
 
@@ -432,7 +430,7 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_phased( const
 				if( lane_idle( l ) && rank < avail ) {
 					seg = blk_next + rank;
 					if( p.perm ) seg = __ldg( p.perm + seg );                       /* binned order (N4): results still land at the segment's own index */
-					lane_load_segment( p, seg, l, side_plane, my_hits );
+					lane_load_segment( p, seg, l );
 				}
 				blk_next += min( n_idle, avail );
 			}
@@ -471,7 +469,7 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_simple( const __grid_cons
 	uint32_t my_hits = 0;
 	for( uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x; seg < p.n; seg += gridDim.x * blockDim.x ) {
 		Lane l;
-		if( !lane_load_segment( p, seg, l, side_plane, my_hits ) ) continue;
+		if( !lane_load_segment( p, seg, l ) ) continue;
 		while( !lane_done( l ) ) {
 			lane_node_phase( map, l, stack, 0xffffffffu );
 			lane_leaf_phase( map, l, stack, 0xffffffffu );
@@ -485,6 +483,42 @@ __global__ void __launch_bounds__( kMaxThreads ) trace_simple( const __grid_cons
 	if( ( threadIdx.x & 31u ) == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
 }
 #endif
+
+/* ---------------------------------------------------------------- the rays the axis shortcut does not cover
+ *
+ * Launched right behind every trace kernel.  When that kernel counted no such ray (the normal case) it returns at once;
+ * otherwise it re-reads the launch's segments, and every ray that is not plain is traced start to finish, from the root,
+ * with the reference's own arithmetic at every node (node_plane_exact: an axis record becomes the unit normal it stands for).
+ * One thread per segment, no scheduling: these rays are rare outside of tests. */
+__global__ void __launch_bounds__( 256 ) trace_exotic_kernel( const __grid_constant__ TraceParams p ) {
+	/* one load per CTA; L1 starts out invalid at a launch boundary, so the plain load sees the count of the kernel before */
+	__shared__ unsigned long long todo_s;
+	if( threadIdx.x == 0 ) todo_s = p.next[ 1 ];
+	__syncthreads();
+	const unsigned long long todo = todo_s;
+	if( todo == 0ull ) return;
+	GlobalMap map;
+	bind_global( p, map );
+	const uint32_t * side_plane = reinterpret_cast< const uint32_t * >( p.image + p.off_side_plane );
+	/* few such rays (the usual case: a coordinate that is exactly 0 turns up about once per 2^24 random floats): their indices
+	 * were listed.  More than the list holds: re-read the launch's segments and pick them out again. */
+	const bool listed = todo <= ( unsigned long long ) kExoticCap;
+	const uint32_t count = listed ? ( uint32_t ) todo : p.n;
+	uint32_t my_hits = 0;
+	for( uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x ) {
+		const uint32_t seg = listed ? p.exotic_list[ i ] : ( p.perm ? __ldg( p.perm + i ) : i );
+		float sx, sy, sz, ex, ey, ez;
+		load_endpoints( p, seg, sx, sy, sz, ex, ey, ez );
+		Ray r; r.sx = sx; r.sy = sy; r.sz = sz; r.dx = ex - sx; r.dy = ey - sy; r.dz = ez - sz;      /* bsp.cc:261 */
+		if( ray_is_plain( r ) ) continue;
+		HitState h;
+		trace_one< GlobalMap, 128 >( map, r, h );
+		store_result( p, seg, r, h, side_plane );
+		my_hits += ( uint32_t ) h.hit;
+	}
+	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( 0xffffffffu, my_hits, o );
+	if( ( threadIdx.x & 31u ) == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
+}
 
 /* ---------------------------------------------------------------- N3: batched position_to_leaf */
 

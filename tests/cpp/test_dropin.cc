@@ -24,9 +24,11 @@ static const Kat kat1[] = {
 static uint32_t bits( float f ) { uint32_t u; memcpy( &u, &f, 4 ); return u; }
 
 int main( int argc, char ** argv ) {
-	if( argc < 2 ) { fprintf( stderr, "usage: %s kat1.bsp\n", argv[ 0 ] ); return 2; }
+	if( argc < 2 ) { fprintf( stderr, "usage: %s kat1.bsp [all]\n", argv[ 0 ] ); return 2; }
 	BSP bsp;
-	bsp_init( &bsp, argv[ 1 ] );
+	/* "all": the map replicated on every GPU of the box, trace_segs sharded across them (bspgpu_multi_*, NCCL hit-count reduction) */
+	if( argc > 2 && !strcmp( argv[ 2 ], "all" ) ) bsp_init( &bsp, argv[ 1 ], BSP_ALL_GPUS );
+	else bsp_init( &bsp, argv[ 1 ] );
 	int bad = 0;
 	const size_t n = sizeof( kat1 ) / sizeof( kat1[ 0 ] );
 

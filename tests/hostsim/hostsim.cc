@@ -30,6 +30,7 @@ std::string g_err;
 
 /* ImageMap that counts record fetches (for sizing the start grid, not used by the parity tests) */
 struct CountingMap {
+	static const bool kGeneralPlanes = true;
 	ImageMap m;
 	mutable uint64_t nodes = 0, refs = 0, sides = 0;
 	void node( int32_t i, float & d, int32_t & c0, int32_t & c1, uint32_t & w ) const { nodes++; m.node( i, d, c0, c1, w ); }

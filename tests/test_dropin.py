@@ -36,6 +36,9 @@ def test_dropin_on_gpu(native, maps, tmp_path):
     _, path = maps("kat1")
     r = subprocess.run([exe, path], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+    # the same program with the map replicated on every GPU of the box (BSP_ALL_GPUS -> bspgpu_multi_*)
+    r = subprocess.run([exe, path, "all"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
 
 
 def _build_depth_frame(native):

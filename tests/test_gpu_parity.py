@@ -132,7 +132,7 @@ def test_host_pipeline_chunks_match_device_path(native, maps, oracle_mod):
     torch.cuda.synchronize()
     res_d = d_out.cpu().numpy().view(native.RESULT_DT).reshape(-1)
     _compare(res_d, d_pos.cpu().numpy(), exp, exp_pos, "device path")
-    assert g.info()["last_launches"] == 1
+    assert g.info()["last_launches"] == 2            # the trace kernel + the (empty) exotic-ray kernel behind it
     g.close()
 
 
@@ -209,7 +209,8 @@ def test_small_batches_and_latency_path(native, maps, oracle_mod):
     """a batch of one (BSP::trace_seg) up to a few thousand segments takes the single-stream bounce-buffer path and
     launches only as many CTAs as there is work for"""
     m, _ = maps("rooms8")
-    segs = _segments(m, 3000, 500, 500, 90)
+    segs = _segments(m, 3000, 600, 600, 200)
+    assert len(segs) >= 4097
     exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
     g = native.BspGpu(m)
     for n in (1, 2, 33, 1000, 4096, 4097):
@@ -370,7 +371,7 @@ def test_multi_launch_and_concurrent_callers(native, maps, oracle_mod):
     g.set_option(12, 40_000)                       # ~6 launches per call
     res = g.trace(segs)
     _compare(res, None, exp, exp_pos, "multi-launch")
-    assert g.info()["last_launches"] == -(-len(segs) // 40_000)
+    assert g.info()["last_launches"] == 2 * -(-len(segs) // 40_000)      # every trace launch is followed by the (usually empty) exotic-ray kernel
     assert g.hit_count() == int((exp["flags"] & 1).sum())
     outs = [None] * 4
 

@@ -31,10 +31,20 @@ def _worker(rank, world, port, n_total, out_path):
     hits = sharding.reduce_hits(torch.tensor([ctr["hits"]], dtype=torch.int64))
     full = sharding.gather_results(local, dst=0)
     slowest = sharding.max_over_ranks(float(rank + 1), "cpu")
+    # the parity sample bench.py takes at every world size: a strided sample of every rank's shard, gathered to rank 0
+    # (over the library's NCCL on the GPUs, over gloo here) and re-traced there by the checker
+    idx = sharding.sample_indices(count, 512)
+    rows = sharding.gather_equal(local[idx].contiguous())
+    srows = sharding.gather_equal(torch.from_numpy(segs)[idx].contiguous())
     if rank == 0:
-        np.savez(out_path, results=full.numpy(), hits=int(hits.item()), first=first, count=count, slowest=slowest)
+        import bench
+        parity = bench.check_sample({"m": m}, srows.reshape(-1, 8).numpy(), rows.reshape(-1, 4).numpy())
+        assert parity["mismatches"] == 0 and parity["checked"] == world * len(idx)
+        broken = rows.clone(); broken[1, 3, 0] ^= 1                       # one flipped bit in one rank's rows must be caught
+        assert bench.check_sample({"m": m}, srows.reshape(-1, 8).numpy(), broken.reshape(-1, 4).numpy())["mismatches"] == 1
+        np.savez(out_path, results=full.numpy(), hits=int(hits.item()), first=first, count=count, slowest=slowest, sampled=parity["checked"])
     else:
-        assert full is None
+        assert full is None and rows is None
     dist.barrier()
     dist.destroy_process_group()
 
