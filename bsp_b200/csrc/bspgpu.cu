@@ -19,6 +19,7 @@
 #include "flatten.h"
 #include "seggen.cuh"
 #include "trace_kernels.cuh"
+#include "pool_kernels.cuh"
 #include "bin_kernels.cuh"
 #include "bspgpu_internal.h"
 
@@ -115,6 +116,19 @@ TraceKernel pick_kernel( int mode, int depth, int threads, int sched, int slots,
 	return mode == kSmemAll ? pick_stack< kSmemAll >( depth, threads, slots, general ) : pick_stack< kGlobal >( depth, threads, slots, general );
 }
 
+/* BSPGPU_OPT_SCHEDULER = 5: CTA-level ray queues (pool_kernels.cuh).  Shapes: threads per CTA, CTAs per SM, pool slots, stack slots in shared memory. */
+struct PoolShape { int threads, rays, stack_slots; uint32_t pool_bytes; TraceKernel kernel[ 2 ]; };
+template< int M, int T, int B, int R, int S >
+PoolShape pool_shape() { return PoolShape{ T, R, S, PoolLayout< R, S >::kBytes, { trace_pool< M, T, B, R, S, false >, trace_pool< M, T, B, R, S, true > } }; }
+const PoolShape * pick_pool( int mode, uint64_t staged, uint64_t smem_cap, int64_t want_threads ) {
+	static const PoolShape global_shapes[] = { pool_shape< kGlobal, 256, 4, 320, 4 >(), pool_shape< kGlobal, 256, 3, 384, 6 >() };
+	static const PoolShape smem_shapes[] = { pool_shape< kSmemAll, 768, 1, 960, 4 >(), pool_shape< kSmemAll, 512, 1, 640, 4 >() };
+	if( mode == kGlobal ) return &global_shapes[ want_threads == 384 ? 1 : 0 ];
+	for( const PoolShape & sh : smem_shapes )
+		if( ( ( staged + 127u ) & ~( uint64_t ) 127u ) + sh.pool_bytes <= smem_cap && ( want_threads <= 0 || want_threads >= sh.threads ) ) return &sh;
+	return nullptr;
+}
+
 } // namespace
 
 namespace {
@@ -137,7 +151,7 @@ int configure( bspgpu * h ) {
 #ifdef BSPGPU_EXPERIMENTS
 	if( h->opt_sched == 4 ) variant = BSPGPU_VARIANT_GLOBAL;   /* the one-thread-per-segment kernel stages nothing */
 #else
-	if( h->opt_sched != 0 ) return fail( BSPGPU_E_INVALID, "BSPGPU_OPT_SCHEDULER: only the phase-scheduled kernel (0) is in this build (others need -DBSPGPU_EXPERIMENTS)" );
+	if( h->opt_sched != 0 && h->opt_sched != 5 ) return fail( BSPGPU_E_INVALID, "BSPGPU_OPT_SCHEDULER: only the phase-scheduled kernel (0) is in this build (others need -DBSPGPU_EXPERIMENTS)" );
 	if( variant == BSPGPU_VARIANT_TOPTREE ) return fail( BSPGPU_E_INVALID, "BSPGPU_VARIANT_TOPTREE needs a -DBSPGPU_EXPERIMENTS build" );
 #endif
 	int mode; uint32_t smem = 0, top_nodes = 0;
@@ -162,6 +176,31 @@ int configure( bspgpu * h ) {
 	const int launch_threads = h->opt_threads > 0 && h->opt_threads < 256 ? ( int ) ( ( h->opt_threads + 31 ) / 32 * 32 ) : threads;
 
 	const uint32_t staged = smem;
+	if( h->opt_sched == 5 ) {
+		if( mode != kGlobal && mode != kSmemAll ) return fail( BSPGPU_E_INVALID, "the queue scheduler runs the SMEM and GLOBAL variants" );
+		if( h->lay.tree_depth > kPoolOverflowDepth ) return fail( BSPGPU_E_INVALID, "the queue scheduler holds traversal stacks of up to 32 entries" );
+		const PoolShape * sh = pick_pool( mode, staged, smem_cap, h->opt_threads );
+		if( !sh ) return fail( BSPGPU_E_INVALID, "the queue scheduler's ray pool does not fit in shared memory beside the staged map" );
+		TraceKernel kernel = sh->kernel[ h->lay.num_gplanes > 0 ? 1 : 0 ];
+		smem = ( ( staged + 127u ) & ~127u ) + sh->pool_bytes;
+		CK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int ) smem ) );
+		int occ = 0;
+		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &occ, kernel, sh->threads, smem ) );
+		if( occ < 1 ) return fail( BSPGPU_E_CUDA, "queue-scheduled kernel does not fit on an SM" );
+		int ctas = ( int ) h->opt_ctas;
+		if( ctas <= 0 || ctas > occ ) ctas = occ;
+		const size_t ovf = ( size_t ) h->sm_count * ctas * sh->rays * kPoolScratchPerRay * sizeof( float4 );
+		if( h->pool_ovf_bytes < ovf ) {
+			if( h->d_pool_ovf ) { CK( cudaDeviceSynchronize() ); cudaFree( h->d_pool_ovf ); h->d_pool_ovf = nullptr; h->pool_ovf_bytes = 0; }
+			CK( cudaMalloc( &h->d_pool_ovf, ovf ) );
+			h->pool_ovf_bytes = ovf;
+		}
+		h->cfg_kernel = kernel; h->cfg_variant = variant; h->cfg_mode = mode; h->cfg_threads = sh->threads; h->cfg_slots = sh->stack_slots; h->cfg_pool_rays = sh->rays;
+		h->cfg_grid = h->sm_count * ctas; h->cfg_smem = smem; h->cfg_staged = staged; h->cfg_top_nodes = 0;
+		h->cfg_valid = true;
+		return BSPGPU_OK;
+	}
+	h->cfg_pool_rays = 0;
 	int slots = 0;
 	int64_t want = h->opt_smem_stack;
 	if( want < 0 ) want = mode == kSmemAll ? 0 : 6;   /* measured: 4 -> +10 %, 6 -> +17 %, 8 -> +10 % on city10k long rays; +-0 behind a staged map */
@@ -204,6 +243,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 	p.leaf_threshold = ( uint32_t ) h->opt_leaf_threshold;
 	p.hits = h->d_counters;
 	p.exotic_list = h->d_exotic;
+	p.pool_overflow = reinterpret_cast< float4 * >( h->d_pool_ovf );
 	p.grid.d = h->lay.grid;
 	const bool use_grid = h->opt_start_grid < 0 ? mode != kSmemAll : h->opt_start_grid != 0;
 	p.grid.cells = ( use_grid && h->lay.grid.dim[ 0 ] ) ? reinterpret_cast< const int32_t * >( h->d_image + h->lay.off_grid ) : nullptr;
@@ -600,6 +640,7 @@ void bspgpu_destroy( bspgpu_t * h ) {
 	if( h->d_exotic ) cudaFree( h->d_exotic );
 	if( h->d_vis ) cudaFree( h->d_vis );
 	if( h->d_scratch ) cudaFree( h->d_scratch );
+	if( h->d_pool_ovf ) cudaFree( h->d_pool_ovf );
 	if( h->h_small ) cudaFreeHost( h->h_small );
 	for( cudaEvent_t ev : { h->ev_start, h->ev_stop, h->ev_pre0, h->ev_pre1, h->ev_user } ) if( ev ) cudaEventDestroy( ev );
 	if( h->own_stream ) cudaStreamDestroy( h->own_stream );
@@ -739,7 +780,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 			/* a claim of zero segments would let a warp spin on the work counter for ever */
 			if( value != 0 && ( value < 32 || value > 65536 ) ) return fail( BSPGPU_E_INVALID, "block segments must be 0 (default) or 32..65536" );
 			h->opt_block_segs = value == 0 ? 256 : ( value + 31 ) / 32 * 32; break;
-		case BSPGPU_OPT_SCHEDULER: if( value != 0 && value != 4 ) return fail( BSPGPU_E_INVALID, "scheduler must be 0 (or 4 in an experiments build)" ); h->opt_sched = value; break;
+		case BSPGPU_OPT_SCHEDULER: if( value != 0 && value != 4 && value != 5 ) return fail( BSPGPU_E_INVALID, "scheduler must be 0, 5 (or 4 in an experiments build)" ); h->opt_sched = value; break;
 		case BSPGPU_OPT_SIDE_STEPS: if( value < 1 || value > 1000000 ) return fail( BSPGPU_E_INVALID, "side steps must be 1..1000000" ); h->opt_side_steps = value; break;
 		case BSPGPU_OPT_LEAF_THRESHOLD: if( value < 1 || value > 32 ) return fail( BSPGPU_E_INVALID, "leaf threshold must be 1..32" ); h->opt_leaf_threshold = value; break;
 		case BSPGPU_OPT_SMEM_STACK: if( value < -1 || value > 8 ) return fail( BSPGPU_E_INVALID, "smem stack slots must be -1 (default), 0, 2, 4, 6 or 8" ); h->opt_smem_stack = value; break;

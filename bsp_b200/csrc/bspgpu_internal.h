@@ -64,7 +64,7 @@ struct bspgpu {
 	/* launch configuration, recomputed only after an option changed */
 	bool cfg_valid = false;
 	TraceKernel cfg_kernel = nullptr;
-	int cfg_variant = 0, cfg_mode = 0, cfg_threads = 0, cfg_grid = 0, cfg_slots = 0;
+	int cfg_variant = 0, cfg_mode = 0, cfg_threads = 0, cfg_grid = 0, cfg_slots = 0, cfg_pool_rays = 0;
 	uint32_t cfg_smem = 0, cfg_staged = 0, cfg_top_nodes = 0;
 
 	/* what the last trace did */
@@ -82,6 +82,8 @@ struct bspgpu {
 	/* grow-only device scratch (leaf queries, segment binning) */
 	void * d_scratch = nullptr;
 	size_t scratch_bytes = 0;
+	void * d_pool_ovf = nullptr;                 /* trace_pool: deep traversal-stack entries (grow-only) */
+	size_t pool_ovf_bytes = 0;
 
 	bool use_user_stream = false;
 	cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }

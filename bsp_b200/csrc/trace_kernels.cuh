@@ -65,6 +65,7 @@ struct TraceParams {
 	unsigned long long * next;        /* work counter, zeroed before launch; next[1] counts the segments left to trace_exotic_kernel */
 	uint32_t * exotic_list;           /* the first kExoticCap of those segments' indices (beyond that the follow-up kernel rescans the launch) */
 	unsigned long long * hits;        /* accumulated hit count */
+	float4 * pool_overflow;           /* trace_pool: global scratch for traversal-stack entries beyond the shared-memory slots */
 };
 
 /* ---------------------------------------------------------------- PTX helpers (TMA bulk copy + mbarrier) */

@@ -644,3 +644,28 @@ def test_smem_stack(native, maps, oracle_mod, name):
             assert g.info()["variant"] == 1 and g.info()["smem_bytes"] > g.info()["staged_bytes"]
             _compare(res, pos, exp, exp_pos, f"{name} staged map + smem stack {slots}")
     g.close()
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("mapname", ["kat1", "rooms8", "city10k", "q3style"])
+def test_queue_scheduler(native, maps, oracle_mod, mapname, variant):
+    """BSPGPU_OPT_SCHEDULER = 5 (pool_kernels.cuh: rays wait in CTA-wide queues, not in lanes) changes where a ray waits,
+    never what is computed: bit-exact against the oracle, for knob settings that force every queue path."""
+    m, path = maps(mapname)
+    g = native.BspGpu(m)
+    if variant == "smem" and g.info()["staged_bytes"] > 120 * 1024:
+        g.close()
+        pytest.skip("no room for the ray pool beside the staged map")
+    g.set_option(1, VARIANTS[variant]); g.set_option(9, 5)
+    segs = _segments(m)
+    exp, exp_pos, ctr = oracle_mod.Port(m).trace(segs)
+    for refill, max_steps, side_steps, leaf_thr in [(8, 0, 3, 16), (1, 1, 1, 1), (32, 1000, 1000, 32), (8, 4, 2, 8)]:
+        g.set_option(6, refill); g.set_option(7, max_steps); g.set_option(10, side_steps); g.set_option(11, leaf_thr)
+        pos = np.zeros((len(segs), 4), np.float32)
+        res = g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos)
+        _compare(res, pos, exp, exp_pos, f"queues {mapname}/{variant} knobs {refill}/{max_steps}/{side_steps}/{leaf_thr}")
+        assert g.hit_count() == ctr["hits"]
+    for n in (1, 33, 4097):
+        res = g.trace(segs[:n].copy())
+        _compare(res, None, exp[:n], exp_pos[:n], f"queues {mapname}/{variant} n={n}")
+    g.close()
