@@ -19,7 +19,9 @@
 #include "flatten.h"
 #include "seggen.cuh"
 #include "trace_kernels.cuh"
+#ifdef BSPGPU_EXPERIMENTS
 #include "pool_kernels.cuh"
+#endif
 #include "bin_kernels.cuh"
 #include "bspgpu_internal.h"
 
@@ -116,7 +118,8 @@ TraceKernel pick_kernel( int mode, int depth, int threads, int sched, int slots,
 	return mode == kSmemAll ? pick_stack< kSmemAll >( depth, threads, slots, general ) : pick_stack< kGlobal >( depth, threads, slots, general );
 }
 
-/* BSPGPU_OPT_SCHEDULER = 5: CTA-level ray queues (pool_kernels.cuh).  Shapes: threads per CTA, CTAs per SM, pool slots, stack slots in shared memory. */
+#ifdef BSPGPU_EXPERIMENTS
+/* BSPGPU_OPT_SCHEDULER = 5: CTA-level ray queues (pool_kernels.cuh; measured slower than the shipped kernel, profiles/README.md).  Shapes: threads per CTA, CTAs per SM, pool slots, stack slots in shared memory. */
 struct PoolShape { int threads, rays, stack_slots; uint32_t pool_bytes; TraceKernel kernel[ 2 ]; };
 template< int M, int T, int B, int R, int S >
 PoolShape pool_shape() { return PoolShape{ T, R, S, PoolLayout< R, S >::kBytes, { trace_pool< M, T, B, R, S, false >, trace_pool< M, T, B, R, S, true > } }; }
@@ -128,6 +131,7 @@ const PoolShape * pick_pool( int mode, uint64_t staged, uint64_t smem_cap, int64
 		if( ( ( staged + 127u ) & ~( uint64_t ) 127u ) + sh.pool_bytes <= smem_cap && ( want_threads <= 0 || want_threads >= sh.threads ) ) return &sh;
 	return nullptr;
 }
+#endif
 
 } // namespace
 
@@ -151,7 +155,7 @@ int configure( bspgpu * h ) {
 #ifdef BSPGPU_EXPERIMENTS
 	if( h->opt_sched == 4 ) variant = BSPGPU_VARIANT_GLOBAL;   /* the one-thread-per-segment kernel stages nothing */
 #else
-	if( h->opt_sched != 0 && h->opt_sched != 5 ) return fail( BSPGPU_E_INVALID, "BSPGPU_OPT_SCHEDULER: only the phase-scheduled kernel (0) is in this build (others need -DBSPGPU_EXPERIMENTS)" );
+	if( h->opt_sched != 0 ) return fail( BSPGPU_E_INVALID, "BSPGPU_OPT_SCHEDULER: only the phase-scheduled kernel (0) is in this build (others need -DBSPGPU_EXPERIMENTS)" );
 	if( variant == BSPGPU_VARIANT_TOPTREE ) return fail( BSPGPU_E_INVALID, "BSPGPU_VARIANT_TOPTREE needs a -DBSPGPU_EXPERIMENTS build" );
 #endif
 	int mode; uint32_t smem = 0, top_nodes = 0;
@@ -176,6 +180,7 @@ int configure( bspgpu * h ) {
 	const int launch_threads = h->opt_threads > 0 && h->opt_threads < 256 ? ( int ) ( ( h->opt_threads + 31 ) / 32 * 32 ) : threads;
 
 	const uint32_t staged = smem;
+#ifdef BSPGPU_EXPERIMENTS
 	if( h->opt_sched == 5 ) {
 		if( mode != kGlobal && mode != kSmemAll ) return fail( BSPGPU_E_INVALID, "the queue scheduler runs the SMEM and GLOBAL variants" );
 		if( h->lay.tree_depth > kPoolOverflowDepth ) return fail( BSPGPU_E_INVALID, "the queue scheduler holds traversal stacks of up to 32 entries" );
@@ -200,6 +205,7 @@ int configure( bspgpu * h ) {
 		h->cfg_valid = true;
 		return BSPGPU_OK;
 	}
+#endif
 	h->cfg_pool_rays = 0;
 	int slots = 0;
 	int64_t want = h->opt_smem_stack;
@@ -780,7 +786,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 			/* a claim of zero segments would let a warp spin on the work counter for ever */
 			if( value != 0 && ( value < 32 || value > 65536 ) ) return fail( BSPGPU_E_INVALID, "block segments must be 0 (default) or 32..65536" );
 			h->opt_block_segs = value == 0 ? 256 : ( value + 31 ) / 32 * 32; break;
-		case BSPGPU_OPT_SCHEDULER: if( value != 0 && value != 4 && value != 5 ) return fail( BSPGPU_E_INVALID, "scheduler must be 0, 5 (or 4 in an experiments build)" ); h->opt_sched = value; break;
+		case BSPGPU_OPT_SCHEDULER: if( value != 0 && value != 4 && value != 5 ) return fail( BSPGPU_E_INVALID, "scheduler must be 0 (or 4 / 5 in an experiments build)" ); h->opt_sched = value; break;
 		case BSPGPU_OPT_SIDE_STEPS: if( value < 1 || value > 1000000 ) return fail( BSPGPU_E_INVALID, "side steps must be 1..1000000" ); h->opt_side_steps = value; break;
 		case BSPGPU_OPT_LEAF_THRESHOLD: if( value < 1 || value > 32 ) return fail( BSPGPU_E_INVALID, "leaf threshold must be 1..32" ); h->opt_leaf_threshold = value; break;
 		case BSPGPU_OPT_SMEM_STACK: if( value < -1 || value > 8 ) return fail( BSPGPU_E_INVALID, "smem stack slots must be -1 (default), 0, 2, 4, 6 or 8" ); h->opt_smem_stack = value; break;

@@ -125,7 +125,8 @@ enum {
 	BSPGPU_OPT_BLOCK_SEGS = 8,      /* consecutive segments a warp claims per global atomic: 0 = default (256), else 32..65536
 	                                   (rounded up to a multiple of 32) */
 	BSPGPU_OPT_SCHEDULER = 9,       /* 0 = phase-scheduled lanes (the shipped kernel).  4 = one thread per segment, no scheduling
-	                                   (experiments build only; the naive baseline) */
+	                                   (experiments build only; the naive baseline).  5 = rays wait in CTA-wide shared-memory queues and
+	                                   warps specialise on node or leaf work (experiments build only: bit-identical, measured 30 % slower) */
 	BSPGPU_OPT_SIDE_STEPS = 10,     /* side steps a lane takes per leaf phase; one step clips two brush sides (default 3) */
 	BSPGPU_OPT_LEAF_THRESHOLD = 11, /* lanes waiting in a leaf that make a warp run a leaf phase (1..32) */
 	BSPGPU_OPT_MAX_LAUNCH_SEGMENTS = 12, /* segments per kernel launch, default and maximum 2^30 (in-kernel indices are 32-bit) */
