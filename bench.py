@@ -303,13 +303,19 @@ def roofline_block(w, bpt, per_gpu, kernel_ms, variant, workload):
     peak, src = peaks[level]
     achieved = bpt["b_map"] * rate / 1e9
     hbm_peak, hbm_src = measured_peak()
-    traffic = None
+    traffic, ncu = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp)).get(workload)
             if tj:
                 traffic = tj["dram_bytes_per_segment"] * per_gpu
+                # what bounds the kernel according to the committed ncu capture of this workload (not measured by this run):
+                # the SM's L1 data pipe moves one wavefront per clock (a scattered 16-byte gather is one wavefront per distinct
+                # line a warp touches, whatever level serves it) and the four schedulers issue one warp instruction per clock each
+                ncu = {k: tj[k] for k in ("l1_data_pipe_pct_of_peak", "issue_slots_pct", "l2_throughput_pct", "lanes_per_instruction",
+                                          "l1_data_pipe_wavefronts_per_segment", "warp_instructions_per_segment", "source") if k in tj}
+                ncu["note"] = "from the committed ncu --set full capture of this workload's kernel (profiles/), per launch of 16 Mi segments"
         except Exception:
             pass
     m = bpt["means"]
@@ -319,6 +325,7 @@ def roofline_block(w, bpt, per_gpu, kernel_ms, variant, workload):
             "peak_source": src, "bytes_per_trace": bpt["b_total"], "bytes_per_trace_map": bpt["b_map"], "bytes_per_trace_io": bpt["b_io"],
             "visit_means": bpt["means"], "visit_means_source": bpt["source"], "kernel_ms": kernel_ms,
             "hbm_stream": {"achieved": bpt["b_io"] * rate / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bpt["b_io"] * rate / 1e9 / hbm_peak, "peak_source": hbm_src},
+            "ncu": ncu,
             "diagnostics": {"record_gathers_per_trace": gathers, "record_gathers_per_s": gathers * rate, "scattered_gather_rate_of_the_level_per_s": gpeak,
                             "note": "record gathers per second against the microbenchmark's fully scattered rate of the same level; lanes share top-of-tree records, so this is a diagnostic, not a ceiling"},
             "note": "achieved = algorithmic map bytes (the records the reference walk touches, BASELINE.md section 5) per second; traffic = DRAM bytes per launch from ncu (the 48 B/segment stream and nothing else)"}
@@ -442,15 +449,19 @@ def run_workload(name, a, local, stream, rank, world, per_gpu, steps, want_e2e):
     return res
 
 
-def link_probe(n_bytes=256 << 20, reps=4):
-    """what this box's host link moves with pinned memory: H2D alone, D2H alone, both at once (per direction)"""
+def link_probe(n_bytes=256 << 20, reps=4, sync=None):
+    """what this box's host link moves with pinned memory: H2D alone, D2H alone, both at once (per direction);
+    sync = a barrier to call before every measurement (all ranks measure the same thing at the same time)"""
     import torch
     h_in = torch.empty(n_bytes, dtype=torch.uint8).pin_memory(); h_out = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
     d_in = torch.empty(n_bytes, dtype=torch.uint8, device="cuda"); d_out = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
     def run(h2d, d2h):
-        torch.cuda.synchronize(); t0 = time.perf_counter()
+        torch.cuda.synchronize()
+        if sync:
+            sync()
+        t0 = time.perf_counter()
         for _ in range(reps):
             if h2d:
                 with torch.cuda.stream(s1):
@@ -553,6 +564,20 @@ def e2e_leg(g, w, a, local, rank, world, segs, out, barrier):
         e2e["link_ceiling"]["segments_per_s_24in_8out"] = min(lc["both_each_gbs"] * 1e9 / 24, lc["both_each_gbs"] * 1e9 / 8)
         e2e["link_ceiling"]["segments_per_s_24in_16out"] = min(lc["both_each_gbs"] * 1e9 / 24, lc["both_each_gbs"] * 1e9 / 16)
         e2e["link_ceiling"]["note"] = "pinned copies on this rank's GPU alone (256 MiB x 4); ceiling = the slower direction at the both-ways rate; other ranks idle while rank 0 probes"
+    if world > 1:
+        # the box's host side is shared: the same probe with every rank copying at once (sums over the ranks)
+        import torch
+        import torch.distributed as dist
+        barrier(); one = link_probe(reps=3, sync=barrier)
+        t = torch.tensor([one["h2d_alone_gbs"], one["d2h_alone_gbs"], one["both_each_gbs"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        if rank == 0:
+            lay = e2e["layouts"][e2e["layout"]]
+            e2e["link_ceiling_all_ranks"] = {
+                "h2d_alone_gbs": t[0].item(), "d2h_alone_gbs": t[1].item(), "both_each_gbs": t[2].item(),
+                "achieved_h2d_gbs": e2e["value"] * lay["h2d_bytes_per_step"] / e2e_n / 1e9, "achieved_d2h_gbs": e2e["value"] * lay["d2h_bytes_per_step"] / e2e_n / 1e9,
+                "note": "all %d ranks copying at once from pinned memory (sum over the ranks, GB/s): input direction alone, output direction alone, "
+                        "both at once (per direction); achieved = what the timed e2e steps moved in each direction" % world}
     lib.bspgpu_host_free(h_in_ptr)
     lib.bspgpu_host_free(h_out_ptr)
     return e2e
