@@ -37,6 +37,51 @@ std::string & bspgpu_err() {
 	return err;
 }
 
+CopyPool::CopyPool( int n ) {
+	for( int i = 0; i < n; i++ ) {
+		workers.emplace_back( [ this ] {
+			for( ;; ) {
+				Task t;
+				{
+					std::unique_lock< std::mutex > lk( m );
+					cv_work.wait( lk, [ this ] { return stop || !q.empty(); } );
+					if( q.empty() ) return;                   /* stop */
+					t = q.front(); q.pop_front();
+				}
+				memcpy( t.dst, t.src, t.bytes );
+				{
+					std::lock_guard< std::mutex > lk( m );
+					if( --pending == 0 ) cv_done.notify_all();
+				}
+			}
+		} );
+	}
+}
+CopyPool::~CopyPool() {
+	{ std::lock_guard< std::mutex > lk( m ); stop = true; }
+	cv_work.notify_all();
+	for( std::thread & w : workers ) w.join();
+}
+void CopyPool::copy( void * dst, const void * src, size_t bytes ) {
+	if( bytes == 0 ) return;
+	const size_t kSlice = 1u << 20;                           /* >= 1 MB per slice, at most one slice per worker and copy */
+	size_t slices = ( bytes + kSlice - 1 ) / kSlice;
+	if( slices > workers.size() ) slices = workers.size();
+	const size_t per = ( ( bytes + slices - 1 ) / slices + 63 ) & ~( size_t ) 63;
+	{
+		std::lock_guard< std::mutex > lk( m );
+		for( size_t off = 0; off < bytes; off += per ) {
+			q.push_back( Task{ ( char * ) dst + off, ( const char * ) src + off, bytes - off < per ? bytes - off : per } );
+			pending++;
+		}
+	}
+	cv_work.notify_all();
+}
+void CopyPool::wait() {
+	std::unique_lock< std::mutex > lk( m );
+	cv_done.wait( lk, [ this ] { return pending == 0; } );
+}
+
 int bspgpu_order_after_user_work( bspgpu * h, cudaStream_t st ) {
 	if( h->user_pending ) { CK( cudaStreamWaitEvent( st, h->ev_user, 0 ) ); h->user_pending = false; }
 	return BSPGPU_OK;
@@ -350,6 +395,83 @@ int ensure_staging( bspgpu * h, size_t segs, bool want_in, bool want_out, bool w
 	return BSPGPU_OK;
 }
 
+/* Pageable caller arrays (what an existing caller of the reference has: std::vector, new[]) cannot be the source or target of an
+ * asynchronous copy -- the driver stages them through one small pinned buffer of its own, synchronously -- and page-locking them
+ * for one call costs more than the call (cudaHostRegister touches every page).  So the library keeps a pinned bounce ring, one
+ * slot per device staging buffer, and a few host threads that copy chunk c+1 from the caller's array into the ring and chunk c-2
+ * out of it while the GPU works on the chunks in between. */
+int ensure_ring( bspgpu * h, size_t segs ) {
+	if( h->ring_segs >= segs ) return BSPGPU_OK;
+	for( int b = 0; b < kBufs; b++ ) {
+		if( h->h_ring_in[ b ] ) cudaFreeHost( h->h_ring_in[ b ] );
+		if( h->h_ring_out[ b ] ) cudaFreeHost( h->h_ring_out[ b ] );
+		if( h->h_ring_pos[ b ] ) cudaFreeHost( h->h_ring_pos[ b ] );
+		h->h_ring_in[ b ] = h->h_ring_out[ b ] = h->h_ring_pos[ b ] = nullptr;
+	}
+	h->ring_segs = 0;
+	for( int b = 0; b < kBufs; b++ ) {
+		CK( cudaMallocHost( &h->h_ring_in[ b ], segs * sizeof( bspgpu_segment ) ) );
+		CK( cudaMallocHost( &h->h_ring_out[ b ], segs * sizeof( bspgpu_result ) ) );
+		CK( cudaMallocHost( &h->h_ring_pos[ b ], segs * sizeof( bspgpu_pos ) ) );
+	}
+	h->ring_segs = segs;
+	if( !h->pool ) {
+		unsigned hw = std::thread::hardware_concurrency();
+		int n = hw >= 16 ? 8 : ( hw >= 4 ? ( int ) hw / 2 : 1 );
+		h->pool = new CopyPool( n );
+	}
+	return BSPGPU_OK;
+}
+
+int trace_bounced( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_pos * pos, bool packed, bool compact, cudaStream_t st ) {
+	const size_t seg_bytes = packed ? 24 : sizeof( bspgpu_segment );
+	const size_t out_bytes = compact ? sizeof( bspgpu_result8 ) : sizeof( bspgpu_result );
+	uint64_t chunk = ( uint64_t ) h->opt_chunk;
+	if( chunk > n ) chunk = n;
+	{ const int rc = ensure_staging( h, ( size_t ) ( chunk < kSmallCall ? kSmallCall : chunk ), true, out != nullptr, pos != nullptr ); if( rc != BSPGPU_OK ) return rc; }
+	{ const int rc = ensure_ring( h, ( size_t ) chunk ); if( rc != BSPGPU_OK ) return rc; }
+	const uint64_t chunks = ( n + chunk - 1 ) / chunk;
+	CK( cudaEventRecord( h->ev_start, st ) );
+	CK( cudaStreamWaitEvent( h->copy_in, h->ev_start, 0 ) );
+	/* iteration c: host copies chunk c into the ring and chunk c-2 out of it (in parallel), then queues chunk c on the GPU */
+	for( uint64_t c = 0; c < chunks + 2; c++ ) {
+		const int b = ( int ) ( c % kBufs );
+		const uint64_t done = c * chunk, cnt = c < chunks ? ( n - done < chunk ? n - done : chunk ) : 0;
+		if( c < chunks ) {
+			if( c >= ( uint64_t ) kBufs ) CK( cudaEventSynchronize( h->ev_in[ b ] ) );                /* the H2D copy that last read this ring slot */
+			h->pool->copy( h->h_ring_in[ b ], ( const char * ) segs + done * seg_bytes, cnt * seg_bytes );
+		}
+		if( c >= 2 ) {
+			const uint64_t d = c - 2, ddone = d * chunk, dcnt = n - ddone < chunk ? n - ddone : chunk;
+			const int db = ( int ) ( d % kBufs );
+			CK( cudaEventSynchronize( h->ev_out[ db ] ) );                                             /* chunk d's results are in the ring */
+			if( out ) h->pool->copy( ( char * ) out + ddone * out_bytes, h->h_ring_out[ db ], dcnt * out_bytes );
+			if( pos ) h->pool->copy( pos + ddone, h->h_ring_pos[ db ], dcnt * sizeof( bspgpu_pos ) );
+		}
+		h->pool->wait();
+		if( c < chunks ) {
+			if( c >= ( uint64_t ) kBufs ) CK( cudaStreamWaitEvent( h->copy_in, h->ev_k[ b ], 0 ) );    /* kernel that last read d_in[b] */
+			CK( cudaMemcpyAsync( h->d_in[ b ], h->h_ring_in[ b ], cnt * seg_bytes, cudaMemcpyHostToDevice, h->copy_in ) );
+			CK( cudaEventRecord( h->ev_in[ b ], h->copy_in ) );
+			CK( cudaStreamWaitEvent( st, h->ev_in[ b ], 0 ) );
+			/* d_out[b] / the ring slot were last used by chunk c-3, whose results left the ring in iteration c-1 */
+			const int rc = enqueue_trace( h, h->d_in[ b ], packed, cnt, out ? h->d_out[ b ] : nullptr, compact, pos ? ( bspgpu_pos * ) h->d_pos[ b ] : nullptr, nullptr, st );
+			if( rc != BSPGPU_OK ) return rc;
+			CK( cudaEventRecord( h->ev_k[ b ], st ) );
+			CK( cudaStreamWaitEvent( h->copy_out, h->ev_k[ b ], 0 ) );
+			if( out ) CK( cudaMemcpyAsync( h->h_ring_out[ b ], h->d_out[ b ], cnt * out_bytes, cudaMemcpyDeviceToHost, h->copy_out ) );
+			if( pos ) CK( cudaMemcpyAsync( h->h_ring_pos[ b ], h->d_pos[ b ], cnt * sizeof( bspgpu_pos ), cudaMemcpyDeviceToHost, h->copy_out ) );
+			CK( cudaEventRecord( h->ev_out[ b ], h->copy_out ) );
+		}
+	}
+	CK( cudaEventRecord( h->ev_stop, st ) );
+	h->timing_valid = true;
+	CK( cudaStreamSynchronize( st ) );
+	CK( cudaStreamSynchronize( h->copy_in ) );
+	CK( cudaStreamSynchronize( h->copy_out ) );
+	return BSPGPU_OK;
+}
+
 /* the hot path behind bspgpu_trace / _pos / _stream; `st` is the stream this call runs on */
 int trace_impl( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_pos * pos, unsigned flags, cudaStream_t st, bool foreign_stream ) {
 	if( n && ( !segs || ( !out && !pos ) ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: null segs, or both out and pos null" );
@@ -403,6 +525,9 @@ int trace_impl( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_po
 
 	/* ---- at least one side lives in host memory: chunked 3-stream pipeline.  Pageable caller memory would make every
 	 *      cudaMemcpyAsync a staged, host-synchronous copy and serialise the pipeline: page-lock it for the call. */
+	if( h->opt_pageable == 2 && !segs_dev && !out_dev && n * seg_bytes >= kPinThresholdBytes
+	    && is_pageable_host( segs ) && ( !out || is_pageable_host( out ) ) && ( !pos || is_pageable_host( pos ) ) )
+		return trace_bounced( h, segs, n, out, pos, packed, compact, st );
 	HostPin pin_in, pin_out, pin_pos;
 	if( h->opt_pageable > 0 ) {
 		if( !segs_dev && n * seg_bytes >= kPinThresholdBytes && is_pageable_host( segs ) ) pin_in.pin( segs, n * seg_bytes, true );
@@ -648,6 +773,8 @@ void bspgpu_destroy( bspgpu_t * h ) {
 	if( h->d_scratch ) cudaFree( h->d_scratch );
 	if( h->d_pool_ovf ) cudaFree( h->d_pool_ovf );
 	if( h->h_small ) cudaFreeHost( h->h_small );
+	for( int b = 0; b < kBufs; b++ ) { if( h->h_ring_in[ b ] ) cudaFreeHost( h->h_ring_in[ b ] ); if( h->h_ring_out[ b ] ) cudaFreeHost( h->h_ring_out[ b ] ); if( h->h_ring_pos[ b ] ) cudaFreeHost( h->h_ring_pos[ b ] ); }
+	delete h->pool;
 	for( cudaEvent_t ev : { h->ev_start, h->ev_stop, h->ev_pre0, h->ev_pre1, h->ev_user } ) if( ev ) cudaEventDestroy( ev );
 	if( h->own_stream ) cudaStreamDestroy( h->own_stream );
 	if( h->copy_in ) cudaStreamDestroy( h->copy_in );
@@ -792,7 +919,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 		case BSPGPU_OPT_SMEM_STACK: if( value < -1 || value > 8 ) return fail( BSPGPU_E_INVALID, "smem stack slots must be -1 (default), 0, 2, 4, 6 or 8" ); h->opt_smem_stack = value; break;
 		case BSPGPU_OPT_START_GRID: h->opt_start_grid = value < 0 ? -1 : ( value ? 1 : 0 ); break;
 		case BSPGPU_OPT_BIN_SEGMENTS: h->opt_bin = value > 0 ? 1 : 0; break;
-		case BSPGPU_OPT_PAGEABLE: h->opt_pageable = value > 0 ? 1 : 0; break;
+		case BSPGPU_OPT_PAGEABLE: if( value < 0 || value > 2 ) return fail( BSPGPU_E_INVALID, "pageable mode must be 0, 1 or 2" ); h->opt_pageable = value; break;
 		case BSPGPU_OPT_MAX_LAUNCH_SEGMENTS:
 			if( value < 32 || ( uint64_t ) value > kMaxLaunchSegs ) return fail( BSPGPU_E_INVALID, "max launch segments must be in [32, 2^30]" );
 			h->opt_max_launch = ( uint64_t ) value; break;

@@ -7,8 +7,12 @@
 
 #include <cuda_runtime.h>
 
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/bspgpu.h"
 #include "map_layout.h"
@@ -30,6 +34,21 @@ struct DeviceGuard {
 		else prev = -1;
 	}
 	~DeviceGuard() { if( prev >= 0 ) cudaSetDevice( prev ); }
+};
+
+/* a few host threads that copy between a caller's pageable arrays and the handle's pinned bounce ring (bspgpu.cu: trace_bounced) */
+struct CopyPool {
+	struct Task { char * dst; const char * src; size_t bytes; };
+	std::vector< std::thread > workers;
+	std::mutex m;
+	std::condition_variable cv_work, cv_done;
+	std::deque< Task > q;
+	size_t pending = 0;
+	bool stop = false;
+	explicit CopyPool( int n );
+	~CopyPool();
+	void copy( void * dst, const void * src, size_t bytes );   /* asynchronous: split into slices for the workers */
+	void wait();                                                  /* until every submitted slice has been copied */
 };
 
 const int kBufs = 3;
@@ -58,7 +77,7 @@ struct bspgpu {
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 16 * 1024;
 	int64_t opt_chunk = 2ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;
 	int64_t opt_sched = 0, opt_side_steps = 3, opt_leaf_threshold = 16;
-	int64_t opt_smem_stack = -1, opt_start_grid = -1, opt_bin = 0, opt_pageable = 1;
+	int64_t opt_smem_stack = -1, opt_start_grid = -1, opt_bin = 0, opt_pageable = 2;
 	uint64_t opt_max_launch = kMaxLaunchSegs;   /* segments per kernel launch (lowered by tests to exercise the multi-launch path) */
 
 	/* launch configuration, recomputed only after an option changed */
@@ -78,6 +97,10 @@ struct bspgpu {
 	size_t buf_segs = 0;
 	cudaEvent_t ev_in[ kBufs ] = { }, ev_k[ kBufs ] = { }, ev_out[ kBufs ] = { };
 	unsigned char * h_small = nullptr;           /* pinned bounce buffer of the small-call path: kSmallCall x (32 + 16 + 16) bytes */
+	/* pageable callers (BSPGPU_OPT_PAGEABLE = 2): pinned bounce ring, one slot per device staging buffer, filled / drained by host threads */
+	void * h_ring_in[ kBufs ] = { }, * h_ring_out[ kBufs ] = { }, * h_ring_pos[ kBufs ] = { };
+	size_t ring_segs = 0;
+	CopyPool * pool = nullptr;
 
 	/* grow-only device scratch (leaf queries, segment binning) */
 	void * d_scratch = nullptr;

@@ -139,7 +139,9 @@ enum {
 	                                   point (a coherence pre-pass) and trace in that order; results still land at each
 	                                   segment's own index.  0 (default) off: measured in profiles/README.md */
 	BSPGPU_OPT_PAGEABLE = 17        /* host-pointer calls with pageable (not page-locked) caller memory:
-	                                   1 (default) = page-lock the caller's arrays for the duration of a large call (cudaHostRegister),
+	                                   2 (default) = bounce through the handle's pinned ring: host threads copy chunk c+1 in and
+	                                       chunk c-2 out while the GPU works on the chunks in between,
+	                                   1 = page-lock the caller's arrays for the duration of a large call (cudaHostRegister),
 	                                   0 = hand them to cudaMemcpyAsync as they are (staged by the driver, serialises the pipeline) */
 };
 

@@ -224,20 +224,33 @@ def test_small_batches_and_latency_path(native, maps, oracle_mod):
 
 
 def test_pageable_callers(native, maps, oracle_mod):
-    """plain (pageable) numpy arrays large enough to be page-locked for the call, with the option on and off"""
+    """plain (pageable) numpy arrays, large enough for the pageable-caller paths: bounced through the pinned ring by host
+    threads (default), page-locked for the call, or left to the driver; 16-byte results + positions, and the packed / compact layouts"""
     m, _ = maps("rooms8")
     from tools import mapgen, seggen
     lo, hi = mapgen.seg_bounds(m)
-    segs = seggen.uniform(31, 0, 1_500_000, lo, hi)                # 48 MB in, 24 MB out
-    exp, _, _ = oracle_mod.Port(m).trace(segs[:300_000])
+    segs = seggen.uniform(31, 0, 1_500_007, lo, hi)                # 48 MB in, 24 MB out; not a multiple of the chunk
+    exp, exp_pos, _ = oracle_mod.Port(m).trace(segs[:300_000])
     g = native.BspGpu(m)
     g.set_option(5, 200_000)
     outs = []
-    for pageable in (1, 0):
+    for pageable in (2, 1, 0):
         g.set_option(17, pageable)
-        outs.append(g.trace(segs))
-        _compare(outs[-1][:300_000], None, exp, None, f"pageable option {pageable}")
-    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+        pos = np.zeros((len(segs), 4), np.float32)
+        outs.append((g.trace(segs, out=np.zeros(len(segs), native.RESULT_DT), pos=pos), pos))
+        _compare(outs[-1][0][:300_000], pos[:300_000], exp, exp_pos, f"pageable option {pageable}")
+    for res, pos in outs[1:]:
+        assert np.array_equal(outs[0][0].view(np.uint32), res.view(np.uint32)) and np.array_equal(bits(outs[0][1]), bits(pos))
+    # the reference's own argument layout (packed vec3 pairs) in, compact records out, through the ring; fewer chunks than ring slots too
+    g.set_option(17, 2)
+    packed = np.ascontiguousarray(np.hstack((segs[:, 0:3], segs[:, 4:7])))
+    for chunk in (200_000, 1_000_000, 2_000_000):
+        g.set_option(5, chunk)
+        r8 = g.trace(packed, out=np.zeros(len(segs), native.RESULT8_DT), packed24=True, compact=True)
+        assert np.array_equal(bits(r8["t"]), bits(outs[0][0]["t"]))
+        assert np.array_equal(r8["bits"], outs[0][0]["flags"] | ((outs[0][0]["plane"] + 1).astype(np.uint32) << 2))
+    with pytest.raises(native.BspGpuError):
+        g.set_option(17, 3)
     g.close()
 
 
