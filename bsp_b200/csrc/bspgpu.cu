@@ -123,32 +123,47 @@ int effective_slots( int mode, int threads, int64_t want ) {
 	const int s = want <= 2 ? 2 : ( want <= 4 ? 4 : ( want <= 6 ? 6 : 8 ) );
 	return threads > 256 && s > 6 ? 6 : s;
 }
+/* GLOBAL variant: lanes walk child slots (trace_slots: the children of a node are gathered while its plane test runs);
+ * SMEM variant: lanes walk node records (trace_phased: with the map in shared memory a gather is 29 cycles and there is
+ * nothing to overlap -- measured +-0).  Experiments builds can put the node-record walk on the GLOBAL variant as well
+ * (BSPGPU_OPT_SCHEDULER = 1), for A/B runs. */
+template< int M, int S, int T, int B, int K, bool G >
+TraceKernel kernel_of( bool node_walk ) {
+	( void ) node_walk;
+	if constexpr( M == kGlobal ) {
+#ifdef BSPGPU_EXPERIMENTS
+		if( node_walk ) return trace_phased< M, S, T, B, K, G >;
+#endif
+		return trace_slots< M, S, T, B, K, G >;
+	}
+	else return trace_phased< M, S, T, B, K, G >;
+}
 template< int M, int S, int T, int B, bool G >
-TraceKernel pick_slots( int slots ) {
+TraceKernel pick_slots( int slots, bool node_walk ) {
 	if constexpr( ( M == kGlobal && T == 256 ) || ( M == kSmemAll && T == 1024 ) ) {
 		switch( slots ) {
-			case 0: return trace_phased< M, S, T, B, 0, G >;
-			case 2: return trace_phased< M, S, T, B, 2, G >;
-			case 4: return trace_phased< M, S, T, B, 4, G >;
-			case 6: return trace_phased< M, S, T, B, 6, G >;
+			case 0: return kernel_of< M, S, T, B, 0, G >( node_walk );
+			case 2: return kernel_of< M, S, T, B, 2, G >( node_walk );
+			case 4: return kernel_of< M, S, T, B, 4, G >( node_walk );
+			case 6: return kernel_of< M, S, T, B, 6, G >( node_walk );
 			default:
-				if constexpr( T == 256 ) return trace_phased< M, S, T, B, 8, G >;
-				else return trace_phased< M, S, T, B, 6, G >;
+				if constexpr( T == 256 ) return kernel_of< M, S, T, B, 8, G >( node_walk );
+				else return kernel_of< M, S, T, B, 6, G >( node_walk );
 		}
 	}
-	else return slots ? trace_phased< M, S, T, B, 6, G > : trace_phased< M, S, T, B, 0, G >;
+	else return slots ? kernel_of< M, S, T, B, 6, G >( node_walk ) : kernel_of< M, S, T, B, 0, G >( node_walk );
 }
 template< int M, int S, bool G >
-TraceKernel pick_threads( int threads, int slots ) {
-	if( threads <= 256 ) return pick_slots< M, S, 256, M == kGlobal ? 5 : 1, G >( slots );
-	if( threads <= 512 ) return pick_slots< M, S, 512, 1, G >( slots );
-	return pick_slots< M, S, 1024, 1, G >( slots );
+TraceKernel pick_threads( int threads, int slots, bool node_walk ) {
+	if( threads <= 256 ) return pick_slots< M, S, 256, M == kGlobal ? 5 : 1, G >( slots, node_walk );
+	if( threads <= 512 ) return pick_slots< M, S, 512, 1, G >( slots, node_walk );
+	return pick_slots< M, S, 1024, 1, G >( slots, node_walk );
 }
 /* depth <= 32: 32-entry local overflow stack; anything deeper (up to the 128 levels bspgpu_create accepts): 128 entries */
 template< int M >
-TraceKernel pick_stack( int depth, int threads, int slots, bool general ) {
-	if( depth <= 32 ) return general ? pick_threads< M, 32, true >( threads, slots ) : pick_threads< M, 32, false >( threads, slots );
-	return general ? pick_threads< M, 128, true >( threads, slots ) : pick_threads< M, 128, false >( threads, slots );
+TraceKernel pick_stack( int depth, int threads, int slots, bool general, bool node_walk ) {
+	if( depth <= 32 ) return general ? pick_threads< M, 32, true >( threads, slots, node_walk ) : pick_threads< M, 32, false >( threads, slots, node_walk );
+	return general ? pick_threads< M, 128, true >( threads, slots, node_walk ) : pick_threads< M, 128, false >( threads, slots, node_walk );
 }
 /* general: the map has node planes that are not axis records */
 TraceKernel pick_kernel( int mode, int depth, int threads, int sched, int slots, bool general ) {
@@ -157,10 +172,9 @@ TraceKernel pick_kernel( int mode, int depth, int threads, int sched, int slots,
 		if( depth <= 32 ) return threads <= 256 ? trace_simple< kGlobal, 32, 256 > : trace_simple< kGlobal, 32, 1024 >;
 		return threads <= 256 ? trace_simple< kGlobal, 128, 256 > : trace_simple< kGlobal, 128, 1024 >;
 	}
-	if( mode == kSmemTop ) return pick_stack< kSmemTop >( depth, threads, slots, general );
+	if( mode == kSmemTop ) return pick_stack< kSmemTop >( depth, threads, slots, general, true );
 #endif
-	( void ) sched;
-	return mode == kSmemAll ? pick_stack< kSmemAll >( depth, threads, slots, general ) : pick_stack< kGlobal >( depth, threads, slots, general );
+	return mode == kSmemAll ? pick_stack< kSmemAll >( depth, threads, slots, general, false ) : pick_stack< kGlobal >( depth, threads, slots, general, sched == 1 );
 }
 
 #ifdef BSPGPU_EXPERIMENTS
@@ -255,7 +269,7 @@ int configure( bspgpu * h ) {
 	int slots = 0;
 	int64_t want = h->opt_smem_stack;
 	if( want < 0 ) want = mode == kSmemAll ? 0 : 6;   /* measured: 4 -> +10 %, 6 -> +17 %, 8 -> +10 % on city10k long rays; +-0 behind a staged map */
-	if( want > 0 && h->opt_sched == 0 ) {
+	if( want > 0 && ( h->opt_sched == 0 || h->opt_sched == 1 ) ) {
 		slots = effective_slots( mode, threads, want );
 		smem = ( smem + 127u ) & ~127u;
 		while( slots > 0 && ( uint64_t ) smem + ( uint64_t ) slots * ( uint32_t ) threads * 16u > smem_cap )   /* smem_cap leaves room for static shared memory */
@@ -296,8 +310,15 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 	p.exotic_list = h->d_exotic;
 	p.pool_overflow = reinterpret_cast< float4 * >( h->d_pool_ovf );
 	p.grid.d = h->lay.grid;
+	p.off_slots = h->lay.off_slots; p.root = h->lay.root;
+	p.g_slot_pairs = reinterpret_cast< const uint4 * >( h->d_image + h->lay.off_slots );
+	p.g_gplanes = reinterpret_cast< const PlaneRec * >( h->d_image + h->lay.off_gplanes );
+	p.g_refs = reinterpret_cast< const BrushRef * >( h->d_image + h->lay.off_refs );
+	p.g_side_pairs = reinterpret_cast< const SideRec * >( h->d_image + h->lay.off_side_pairs );
+	p.g_side_plane = reinterpret_cast< const uint32_t * >( h->d_image + h->lay.off_side_plane );
 	const bool use_grid = h->opt_start_grid < 0 ? mode != kSmemAll : h->opt_start_grid != 0;
 	p.grid.cells = ( use_grid && h->lay.grid.dim[ 0 ] ) ? reinterpret_cast< const int32_t * >( h->d_image + h->lay.off_grid ) : nullptr;
+	p.grid_slots = p.grid.cells ? reinterpret_cast< const Slot * >( h->d_image + h->lay.off_grid_slots ) : nullptr;
 
 	h->last_variant = ( uint32_t ) h->cfg_variant; h->last_threads = ( uint32_t ) threads; h->last_smem = smem; h->last_slots = ( uint32_t ) h->cfg_slots;
 
@@ -913,7 +934,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 			/* a claim of zero segments would let a warp spin on the work counter for ever */
 			if( value != 0 && ( value < 32 || value > 65536 ) ) return fail( BSPGPU_E_INVALID, "block segments must be 0 (default) or 32..65536" );
 			h->opt_block_segs = value == 0 ? 256 : ( value + 31 ) / 32 * 32; break;
-		case BSPGPU_OPT_SCHEDULER: if( value != 0 && value != 4 && value != 5 ) return fail( BSPGPU_E_INVALID, "scheduler must be 0 (or 4 / 5 in an experiments build)" ); h->opt_sched = value; break;
+		case BSPGPU_OPT_SCHEDULER: if( value != 0 && value != 1 && value != 4 && value != 5 ) return fail( BSPGPU_E_INVALID, "scheduler must be 0 (or 1 / 4 / 5 in an experiments build)" ); h->opt_sched = value; break;
 		case BSPGPU_OPT_SIDE_STEPS: if( value < 1 || value > 1000000 ) return fail( BSPGPU_E_INVALID, "side steps must be 1..1000000" ); h->opt_side_steps = value; break;
 		case BSPGPU_OPT_LEAF_THRESHOLD: if( value < 1 || value > 32 ) return fail( BSPGPU_E_INVALID, "leaf threshold must be 1..32" ); h->opt_leaf_threshold = value; break;
 		case BSPGPU_OPT_SMEM_STACK: if( value < -1 || value > 8 ) return fail( BSPGPU_E_INVALID, "smem stack slots must be -1 (default), 0, 2, 4, 6 or 8" ); h->opt_smem_stack = value; break;

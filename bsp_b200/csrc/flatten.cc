@@ -282,8 +282,32 @@ int flatten_map( const bspgpu_map_desc & L, const FlattenOptions & opt, FlatMap 
 			}
 		}
 	}
-	lay.total_bytes = align_up( lay.off_grid + ( uint64_t ) grid_cells.size() * sizeof( int32_t ), kSectionAlign );
-	if( lay.total_bytes == 0 ) lay.total_bytes = kSectionAlign;
+	/* ---- child slots (map_layout.h: Slot): pair i + 1 = the two children of breadth-first node i, pair 0 = { root, unused } */
+	if( num_nodes >= ( 1u << 29 ) - 2u ) { err = "too many nodes"; return BSPGPU_E_MAP; }
+	auto node_slot = [&]( uint32_t i ) -> Slot {
+		const NodeRec & n = onodes[ i ];
+		Slot s;
+		if( n.w < kGeneralPlane ) { memcpy( &s.a, &n.d, 4 ); s.x = ( ( i + 1 ) << 3 ) | n.w; }
+		else { s.a = n.w - kGeneralPlane; s.x = ( ( i + 1 ) << 3 ) | kSlotGeneral; }
+		return s;
+	};
+	auto child_slot = [&]( int32_t c ) -> Slot {
+		if( c >= 0 ) return node_slot( ( uint32_t ) c );
+		Slot s;
+		if( c == kEmptyLeaf ) { s.a = 0xffffffffu; s.x = kSlotEmpty; }
+		else { s.a = ( uint32_t ) ~c; s.x = kSlotLeaf; }
+		return s;
+	};
+	std::vector< Slot > oslots( 2 * ( ( size_t ) num_nodes + 1 ) );
+	oslots[ 0 ] = node_slot( 0 );
+	oslots[ 1 ].a = 0xffffffffu; oslots[ 1 ].x = kSlotEmpty;
+	for( uint32_t i = 0; i < num_nodes; i++ ) for( int k = 0; k < 2; k++ ) oslots[ 2 * ( ( size_t ) i + 1 ) + k ] = child_slot( onodes[ i ].child[ k ] );
+	lay.root = oslots[ 0 ];
+	std::vector< Slot > grid_slots( grid_cells.size() );
+	for( size_t i = 0; i < grid_cells.size(); i++ ) grid_slots[ i ] = grid_cells[ i ] == 0 ? oslots[ 0 ] : child_slot( grid_cells[ i ] );
+	lay.off_slots = align_up( lay.off_grid + ( uint64_t ) grid_cells.size() * sizeof( int32_t ), kSectionAlign );
+	lay.off_grid_slots = align_up( lay.off_slots + ( uint64_t ) oslots.size() * sizeof( Slot ), kSectionAlign );
+	lay.total_bytes = align_up( lay.off_grid_slots + ( uint64_t ) grid_slots.size() * sizeof( Slot ), kSectionAlign );
 
 	out.image.assign( lay.total_bytes, 0 );
 	unsigned char * img = out.image.data();
@@ -299,6 +323,8 @@ int flatten_map( const bspgpu_map_desc & L, const FlattenOptions & opt, FlatMap 
 	memcpy( img + lay.off_node_orig, oorig.data(), oorig.size() * sizeof( NodeOrig ) );
 	for( uint32_t i = 0; i < L.num_leaves; i++ ) memcpy( img + lay.off_leaf_cluster + ( uint64_t ) i * 4, &leaves[ i ].cluster, 4 );
 	if( !grid_cells.empty() ) memcpy( img + lay.off_grid, grid_cells.data(), grid_cells.size() * sizeof( int32_t ) );
+	memcpy( img + lay.off_slots, oslots.data(), oslots.size() * sizeof( Slot ) );
+	if( !grid_slots.empty() ) memcpy( img + lay.off_grid_slots, grid_slots.data(), grid_slots.size() * sizeof( Slot ) );
 	return BSPGPU_OK;
 }
 

@@ -64,6 +64,22 @@ struct alignas( 16 ) BrushRef {
 	uint32_t reserved;
 };
 
+/* Child slots: what the trace kernels walk.  Every child of every node -- internal node or leaf -- owns one 8-byte slot, and
+ * the two children of a node sit side by side in one 16-byte pair, so ONE 16-byte gather fetches both children of the node
+ * being tested while its plane test is still running (the plane of a node travels in the slot that points to it, not in a
+ * record of its own): the dependent chain of a step is max(gather, plane test), not their sum.
+ *   x & 7 = 0, 1, 2   internal node whose plane normal is bitwise +e_x / +e_y / +e_z: a = bits of the plane's d
+ *   x & 7 = 4         internal node with any other plane: a = index into gplanes (which carries n and d)
+ *                     in both cases x >> 3 = index of the pair that holds the node's children (breadth-first index + 1;
+ *                     pair 0 = { root, unused })
+ *   x == kSlotLeaf    leaf with solid brushes: a = index of its first BrushRef
+ *   x == kSlotEmpty   leaf without solid brushes
+ * kSlotDone / kSlotIdle never appear in the image: they are the two other states of a kernel lane. */
+struct alignas( 8 ) Slot {
+	uint32_t a, x;
+};
+static const uint32_t kSlotGeneral = 4, kSlotLeaf = 3, kSlotEmpty = 7, kSlotDone = 11, kSlotIdle = 15;
+
 static const int32_t kEmptyLeaf = INT32_MIN;
 static const uint32_t kLastRef = 0x80000000u;
 static const uint32_t kSectionAlign = 128;
@@ -85,6 +101,8 @@ struct MapImageLayout {
 	uint64_t off_nodes, off_gplanes, off_refs, off_sides_even, off_sides_odd;   /* the staged prefix */
 	uint64_t off_side_pairs, off_side_plane, off_node_orig, off_leaf_cluster, off_grid, total_bytes;
 	uint64_t staged_bytes;   /* prefix the whole-map variant copies to shared memory */
+	uint64_t off_slots, off_grid_slots;   /* child slots in pairs (2 * (num_nodes + 1) slots); start grid as slots (8 B per cell) */
+	Slot root;               /* the slot of node 0: where every walk starts (bsp.cc:263) */
 	StartGridDesc grid;
 };
 

@@ -250,6 +250,7 @@ static const int32_t kCurIdle = INT32_MIN;        /* == kEmptyLeaf, which is nev
 static const int32_t kCurDone = INT32_MIN + 1;
 static const uint32_t kBrushHit = 1u, kBrushInside = 2u, kBrushLastRef = 4u;
 static const uint32_t kHitFlag = 1u, kStartSolidFlag = 2u;
+static const uint32_t kSlotHit = 8u, kSlotStartSolid = 16u;   /* the same two flags where LaneS keeps them: beside the brush flags */
 
 struct alignas( 16 ) StackEntry16 {
 	int32_t node;
@@ -427,7 +428,8 @@ BSPK_HD void lane_node_phase( const Map & map, Lane & l, const Stack & stack, ui
 
 /* one turn of trace_seg_brush's side loop (bsp.cc:128-165) for side `index` with plane (n, d); `live` = false leaves the
  * lane untouched.  Returns whether the side rejected the brush (:135). */
-BSPK_HD bool lane_side_apply( Lane & l, float ex, float ey, float ez, int32_t index, bool live, float nx, float ny, float nz, float d ) {
+template< class LaneT >
+BSPK_HD bool lane_side_apply( LaneT & l, float ex, float ey, float ez, int32_t index, bool live, float nx, float ny, float nz, float d ) {
 	const float start_dist = dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz ) - d;    /* :131 */
 	const float end_dist = dot3( ex, ey, ez, nx, ny, nz ) - d;                  /* :132 */
 	const float denom = -dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );           /* :141 */
@@ -527,6 +529,256 @@ BSPK_HD void trace_one_phased( const Map & map, float sx, float sy, float sz, fl
 	lane_hit_state( l, h_out );
 }
 
+/* ------------------------------------------------------------------------------------------
+ * The same resumable walk over CHILD SLOTS (map_layout.h: Slot) -- what the shipped kernels run.
+ *
+ * A lane carries the slot it is visiting {ca, cx}: plane + where the children are for an internal node, first brush
+ * reference for a leaf.  A node step first issues the 16-byte gather of the node's two child slots, then runs the plane
+ * test on what it already holds, and only then selects near / far from the pair: the gather of step k + 1 no longer waits
+ * for the division of step k.  Pending far sides are pushed as whole slots {x, a, tmin, tmax} (16 bytes), so a pop touches
+ * no map record either.  Every fp32 operation and comparison is the one lane_node_apply / lane_leaf_phase above perform.
+ * ------------------------------------------------------------------------------------------ */
+struct LaneS {
+	Ray r;
+	float tmin, tmax;
+	uint32_t ca, cx;      /* the slot being visited; cx also encodes done / idle (kSlotDone / kSlotIdle) */
+	int32_t sp;
+	float ht;
+	int32_t hside, hbrush;
+	uint32_t s, s_end;
+	uint32_t bflags;      /* kBrushHit | kBrushInside | kBrushLastRef of the brush being clipped, and the running result's
+	                         kSlotHit | kSlotStartSolid (one register for both sets) */
+	float tfar, tnear;
+	int32_t far_side;
+};
+
+BSPK_HD bool slane_in_node( const LaneS & l ) { return ( l.cx & 3u ) != 3u; }
+BSPK_HD bool slane_in_leaf( const LaneS & l ) { return l.cx == kSlotLeaf; }
+BSPK_HD bool slane_done( const LaneS & l ) { return l.cx == kSlotDone; }
+BSPK_HD bool slane_idle( const LaneS & l ) { return l.cx == kSlotIdle; }
+
+BSPK_HD float bits_to_float( uint32_t b ) {
+#ifdef __CUDA_ARCH__
+	return __uint_as_float( b );
+#else
+	float f; memcpy( &f, &b, 4 ); return f;
+#endif
+}
+
+struct alignas( 16 ) SlotEntry {
+	uint32_t x, a;
+	float tmin, tmax;
+};
+BSPK_HD void sstack_put( SlotEntry * s, int32_t i, uint32_t x, uint32_t a, float tmin, float tmax ) {
+	s[ i ].x = x; s[ i ].a = a; s[ i ].tmin = tmin; s[ i ].tmax = tmax;
+}
+BSPK_HD void sstack_get( const SlotEntry * s, int32_t i, uint32_t & x, uint32_t & a, float & tmin, float & tmax ) {
+	const SlotEntry e = s[ i ];
+	x = e.x; a = e.a; tmin = e.tmin; tmax = e.tmax;
+}
+template< int D >
+struct SplitSlotStack {
+	SlotEntry * lo, * hi;
+};
+template< int D >
+BSPK_HD void sstack_put( const SplitSlotStack< D > & s, int32_t i, uint32_t x, uint32_t a, float tmin, float tmax ) {
+	if( i < D ) sstack_put( s.lo, i, x, a, tmin, tmax );
+	else sstack_put( s.hi, i - D, x, a, tmin, tmax );
+}
+template< int D >
+BSPK_HD void sstack_get( const SplitSlotStack< D > & s, int32_t i, uint32_t & x, uint32_t & a, float & tmin, float & tmax ) {
+	if( i < D ) sstack_get( s.lo, i, x, a, tmin, tmax );
+	else sstack_get( s.hi, i - D, x, a, tmin, tmax );
+}
+
+struct SlotGrid {
+	const Slot * cells;   /* null = disabled */
+	StartGridDesc d;
+};
+
+BSPK_HD void slane_start( LaneS & l, float sx, float sy, float sz, float ex, float ey, float ez ) {
+	l.r.sx = sx; l.r.sy = sy; l.r.sz = sz;
+	l.r.dx = ex - sx; l.r.dy = ey - sy; l.r.dz = ez - sz;      /* bsp.cc:261 */
+	l.ht = 1.0f; l.hside = -1; l.hbrush = -1;                    /* bsp.cc:256-257 */
+	l.tmin = 0.0f; l.tmax = 1.0f; l.sp = 0;                      /* bsp.cc:263 */
+	l.s = 0; l.s_end = 0;
+	l.bflags = 0; l.tfar = 0.0f; l.tnear = 0.0f; l.far_side = -1;
+}
+
+/* the slot where the walk of segment (s, e) may start: the root's (bsp.cc:263), or -- both endpoints in one start-grid cell --
+ * the one stored for that cell (same lookup and same guarantees as grid_start_ref above) */
+BSPK_HD Slot grid_start_slot( const SlotGrid & g, const Slot & root, float sx, float sy, float sz, float ex, float ey, float ez ) {
+	if( !g.cells ) return root;
+	const StartGridDesc & d = g.d;
+	const float cx = floorf( ( sx - d.lo[ 0 ] ) * d.inv[ 0 ] ), cy = floorf( ( sy - d.lo[ 1 ] ) * d.inv[ 1 ] ), cz = floorf( ( sz - d.lo[ 2 ] ) * d.inv[ 2 ] );
+	const float ox = floorf( ( ex - d.lo[ 0 ] ) * d.inv[ 0 ] ), oy = floorf( ( ey - d.lo[ 1 ] ) * d.inv[ 1 ] ), oz = floorf( ( ez - d.lo[ 2 ] ) * d.inv[ 2 ] );
+	const bool same = cx == ox && cy == oy && cz == oz;
+	const bool inside = cx >= 0.0f && cx < ( float ) d.dim[ 0 ] && cy >= 0.0f && cy < ( float ) d.dim[ 1 ] && cz >= 0.0f && cz < ( float ) d.dim[ 2 ];
+	if( !( same && inside ) ) return root;
+	const int32_t ix = ( int32_t ) cx, iy = ( int32_t ) cy, iz = ( int32_t ) cz;
+#ifdef __CUDA_ARCH__
+	const uint2 v = __ldg( reinterpret_cast< const uint2 * >( g.cells + ( uint32_t ) ( ( iz * d.dim[ 1 ] + iy ) * d.dim[ 0 ] + ix ) ) );
+	Slot s; s.a = v.x; s.x = v.y;
+	return s;
+#else
+	return g.cells[ ( uint32_t ) ( ( iz * d.dim[ 1 ] + iy ) * d.dim[ 0 ] + ix ) ];
+#endif
+}
+
+BSPK_HD void slane_start_at( LaneS & l, const Slot & s ) {
+	l.ca = s.a;
+	l.cx = s.x == kSlotEmpty ? kSlotDone : s.x;   /* the whole segment lies in a leaf without solid brushes: a miss, t = 1 */
+}
+
+BSPK_HD void slane_hit_state( const LaneS & l, HitState & h ) {
+	h.t = l.ht; h.hit = ( l.bflags & kSlotHit ) ? 1 : 0; h.startsolid = ( l.bflags & kSlotStartSolid ) ? 1 : 0;
+	h.far_side = l.hside; h.brush = l.hbrush;
+}
+
+/* component (0, 1, 2) of the ray's start and direction named by the low bits of a node slot's x (see ray_axis) */
+BSPK_HD void ray_axis_bits( const Ray & r, uint32_t x, float & s, float & d ) {
+#ifdef __CUDA_ARCH__
+	asm( "{\n\t.reg .pred p1, p2;\n\t.reg .b32 t1, t2;\n\tand.b32 t1, %2, 1;\n\tand.b32 t2, %2, 2;\n\tsetp.ne.u32 p1, t1, 0;\n\tsetp.ne.u32 p2, t2, 0;\n\t"
+	     "selp.f32 %0, %4, %3, p1;\n\tselp.f32 %0, %5, %0, p2;\n\tselp.f32 %1, %7, %6, p1;\n\tselp.f32 %1, %8, %1, p2;\n\t}"
+	     : "=&f"( s ), "=&f"( d ) : "r"( x ), "f"( r.sx ), "f"( r.sy ), "f"( r.sz ), "f"( r.dx ), "f"( r.dy ), "f"( r.dz ) );
+#else
+	s = ( x & 2u ) ? r.sz : ( ( x & 1u ) ? r.sy : r.sx );
+	d = ( x & 2u ) ? r.dz : ( ( x & 1u ) ? r.dy : r.dx );
+#endif
+}
+
+/* one trace_seg_tree step (bsp.cc:213-252) at the internal node whose slot the lane holds; the lane's ray must be plain */
+template< class Map, class Stack >
+BSPK_HD void slane_node_step( const Map & map, LaneS & l, const Stack & stack ) {
+	uint32_t a0, x0, a1, x1;
+	map.pair( l.cx >> 3, a0, x0, a1, x1 );                                         /* children[ 0 ], children[ 1 ]: needed last, asked for first */
+	float denom, sdot, d;
+	if( !Map::kGeneralPlanes || ( l.cx & kSlotGeneral ) == 0u ) {
+		ray_axis_bits( l.r, l.cx, sdot, denom );                                   /* = dot( start, e_w ) :221, dot( e_w, dir ) :220 */
+		d = bits_to_float( l.ca );
+	}
+	else {
+		float nx, ny, nz;
+		map.gplane_d( l.ca, nx, ny, nz, d );
+		denom = dot3( nx, ny, nz, l.r.dx, l.r.dy, l.r.dz );                        /* :220 */
+		sdot = dot3( l.r.sx, l.r.sy, l.r.sz, nx, ny, nz );
+	}
+	const float dist = -( sdot - d );                                              /* :221 */
+	const float u = dist / denom;                                                  /* :227 */
+	const bool in_range = denom != 0.0f && u >= 0.0f && u <= l.tmax;               /* :226,:232 */
+	const bool below = u < l.tmin;                                                 /* :235 */
+	const bool both = in_range && !below;                                          /* :238 */
+	const bool near_back = ( dist > 0.0f ) != ( in_range && below );               /* :222,:236 */
+	const uint32_t an = near_back ? a1 : a0, xn = near_back ? x1 : x0;             /* children[ near ] */
+	const uint32_t af = near_back ? a0 : a1, xf = near_back ? x0 : x1;             /* children[ !near ] */
+	const bool near_ok = xn != kSlotEmpty;
+	const bool far_work = both && xf != kSlotEmpty;
+	const bool do_push = near_ok && far_work;
+	const bool do_pop = !near_ok && !far_work;
+	const bool can_pop = do_pop && l.sp > 0;
+	if( do_push ) {
+		sstack_put( stack, l.sp, xf, af, u, l.tmax );
+		l.sp++;
+	}
+	l.ca = near_ok ? an : af;
+	l.cx = near_ok ? xn : xf;
+	l.tmax = ( near_ok && both ) ? u : l.tmax;
+	l.tmin = near_ok ? l.tmin : u;
+	if( do_pop ) l.cx = kSlotDone;
+	if( can_pop ) {
+		l.sp--;
+		sstack_get( stack, l.sp, l.cx, l.ca, l.tmin, l.tmax );
+	}
+}
+
+template< class Map, class Stack >
+BSPK_HD void slane_node_phase( const Map & map, LaneS & l, const Stack & stack, uint32_t max_steps ) {
+	if( !slane_in_node( l ) ) return;
+	for( ; max_steps > 0 && slane_in_node( l ); max_steps-- ) {
+		slane_node_step( map, l, stack );
+	}
+	l.s = 0; l.s_end = 0;                                                          /* if the walk reached a leaf: fetch its first brush reference */
+}
+
+/* lane_leaf_phase over slots: in leaf mode ca is the brush reference being clipped */
+template< class Map, class Stack >
+BSPK_HD void slane_leaf_phase( const Map & map, LaneS & l, const Stack & stack, uint32_t max_steps ) {
+	float ex = l.r.sx + l.r.dx * l.tmax, ey = l.r.sy + l.r.dy * l.tmax, ez = l.r.sz + l.r.dz * l.tmax;   /* bsp.cc:121 */
+	for( ; max_steps > 0 && slane_in_leaf( l ); max_steps-- ) {
+		if( l.s == l.s_end ) {
+			uint32_t first, nraw; int32_t brush;
+			map.ref( l.ca, first, nraw, brush );
+			l.s = first; l.s_end = first + ( nraw & ~kLastRef );
+			l.bflags = ( l.bflags & ( kSlotHit | kSlotStartSolid ) ) | kBrushInside | ( ( nraw & kLastRef ) ? kBrushLastRef : 0u );
+			l.tfar = l.tmin; l.tnear = l.tmax; l.far_side = -1;                         /* bsp.cc:122-125 */
+		}
+		float n0x, n0y, n0z, d0, n1x, n1y, n1z, d1;
+		map.side_pair( l.s, n0x, n0y, n0z, d0, n1x, n1y, n1z, d1 );
+		bool rejected = lane_side_apply( l, ex, ey, ez, ( int32_t ) l.s, true, n0x, n0y, n0z, d0 );
+		rejected = lane_side_apply( l, ex, ey, ez, ( int32_t ) l.s + 1, !rejected, n1x, n1y, n1z, d1 ) || rejected;
+		l.s += 2;
+		if( !rejected && l.s != l.s_end ) continue;
+
+		/* ---- brush over: bsp.cc:169-182 folded into :197-200 */
+		if( !rejected ) {
+			const bool inside = ( l.bflags & kBrushInside ) != 0;
+			if( inside ) l.bflags |= kSlotStartSolid;
+			const bool brush_hit = ( l.bflags & kBrushHit ) && ( inside ? ( l.tnear < l.tfar ) : ( l.tfar <= l.tnear ) );   /* :171,:176 */
+			if( brush_hit ) {
+				const float bt = inside ? l.tnear : l.tfar;
+				if( !( l.bflags & kSlotHit ) || bt < l.ht ) {
+					/* the brush index is not carried through the side loop: its reference is read again on the (rare) hit */
+					uint32_t first, nraw;
+					l.hside = inside ? -1 : l.far_side; map.ref( l.ca, first, nraw, l.hbrush );
+				}
+				l.bflags |= kSlotHit;                                               /* :198 */
+				if( bt < l.ht ) l.ht = bt;                                          /* :199 */
+			}
+		}
+		l.s = l.s_end;
+		if( !( l.bflags & kBrushLastRef ) ) { l.ca++; continue; }                   /* next brush reference of this leaf */
+
+		/* ---- leaf over: a hit ends the whole trace (bsp.cc:206), otherwise the next pending far side */
+		if( l.bflags & kSlotHit ) { l.cx = kSlotDone; break; }
+		if( l.sp == 0 ) { l.cx = kSlotDone; break; }
+		l.sp--;
+		sstack_get( stack, l.sp, l.cx, l.ca, l.tmin, l.tmax );
+		l.s = 0; l.s_end = 0;
+		ex = l.r.sx + l.r.dx * l.tmax; ey = l.r.sy + l.r.dy * l.tmax; ez = l.r.sz + l.r.dz * l.tmax;
+	}
+}
+
+/* trace_one through the slot walk (budgets make no difference to the result); kSplit > 0 keeps the first kSplit stack
+ * entries in a separate array, the way the kernels keep them in shared memory */
+template< class Map, int kStack, int kSplit = 0 >
+BSPK_HD void trace_one_slots( const Map & map, const Slot & root, float sx, float sy, float sz, float ex, float ey, float ez,
+                              uint32_t node_budget, uint32_t side_budget, Ray & r_out, HitState & h_out, const SlotGrid * grid = nullptr ) {
+	SlotEntry stack[ kStack ];
+	SlotEntry low[ kSplit > 0 ? kSplit : 1 ];
+	LaneS l;
+	slane_start( l, sx, sy, sz, ex, ey, ez );
+	if( !ray_is_plain( l.r ) ) {                       /* as the kernels do: such a ray takes the general arithmetic start to finish */
+		r_out = l.r;
+		trace_one< Map, kStack >( map, l.r, h_out );
+		return;
+	}
+	slane_start_at( l, grid ? grid_start_slot( *grid, root, sx, sy, sz, ex, ey, ez ) : root );
+	while( !slane_done( l ) ) {
+		if constexpr( kSplit > 0 ) {
+			SplitSlotStack< kSplit > st; st.lo = low; st.hi = stack;
+			slane_node_phase( map, l, st, node_budget );
+			slane_leaf_phase( map, l, st, side_budget );
+		}
+		else {
+			SlotEntry * st = stack;
+			slane_node_phase( map, l, st, node_budget );
+			slane_leaf_phase( map, l, st, side_budget );
+		}
+	}
+	r_out = l.r;
+	slane_hit_state( l, h_out );
+}
+
 /* BSP::position_to_leaf (bsp.cc:273-286) on the flattened nodes; returns the file's leaf index */
 template< class Map >
 BSPK_HD int32_t point_leaf( const Map & map, float px, float py, float pz ) {
@@ -576,6 +828,14 @@ struct ImageMap {
 	const BrushRef * refs;
 	const SideRec * side_pairs;
 	const NodeOrig * node_orig;
+	const Slot * slots;
+	BSPK_HD void pair( uint32_t p, uint32_t & a0, uint32_t & x0, uint32_t & a1, uint32_t & x1 ) const {
+		a0 = slots[ 2 * p ].a; x0 = slots[ 2 * p ].x; a1 = slots[ 2 * p + 1 ].a; x1 = slots[ 2 * p + 1 ].x;
+	}
+	BSPK_HD void gplane_d( uint32_t i, float & nx, float & ny, float & nz, float & d ) const {
+		const PlaneRec & p = gplanes[ i ];
+		nx = p.nx; ny = p.ny; nz = p.nz; d = p.d;
+	}
 	BSPK_HD void node( int32_t i, float & d, int32_t & c0, int32_t & c1, uint32_t & w ) const {
 		const NodeRec & n = nodes[ i ];
 		d = n.d; c0 = n.child[ 0 ]; c1 = n.child[ 1 ]; w = n.w;

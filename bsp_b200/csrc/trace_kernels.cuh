@@ -62,6 +62,12 @@ struct TraceParams {
 	uint32_t side_steps;              /* side steps per lane per leaf phase */
 	uint32_t leaf_threshold;          /* lanes waiting in a leaf that make the warp run a leaf phase */
 	StartGrid grid;                   /* cells == null: every walk starts at node 0 */
+	uint64_t off_slots;               /* child slots (map_layout.h: Slot) */
+	/* the same sections as absolute pointers: under register pressure the compiler re-derives a base from the constant bank
+	 * inside the hot loops, and image + offset is five instructions where a pointer parameter is two */
+	const uint4 * g_slot_pairs; const PlaneRec * g_gplanes; const BrushRef * g_refs; const SideRec * g_side_pairs; const uint32_t * g_side_plane;
+	Slot root;                        /* slot of node 0 */
+	const Slot * grid_slots;          /* start grid as slots, or null */
 	unsigned long long * next;        /* work counter, zeroed before launch; next[1] counts the segments left to trace_exotic_kernel */
 	uint32_t * exotic_list;           /* the first kExoticCap of those segments' indices (beyond that the follow-up kernel rescans the launch) */
 	unsigned long long * hits;        /* accumulated hit count */
@@ -176,6 +182,16 @@ struct GlobalMap {
 	static const bool kGeneralPlanes = true;
 	const NodeRec * nodes; const PlaneRec * gplanes; const BrushRef * refs; const SideRec * side_pairs;   /* global memory, read-only path */
 	const NodeOrig * node_orig;
+	const uint4 * slot_pairs;
+	/* both child slots of a node in one 16-byte read-only gather */
+	__device__ __forceinline__ void pair( uint32_t p, uint32_t & a0, uint32_t & x0, uint32_t & a1, uint32_t & x1 ) const {
+		const uint4 r = __ldg( slot_pairs + p );
+		a0 = r.x; x0 = r.y; a1 = r.z; x1 = r.w;
+	}
+	__device__ __forceinline__ void gplane_d( uint32_t i, float & nx, float & ny, float & nz, float & d ) const {
+		const float4 p = __ldg( reinterpret_cast< const float4 * >( &gplanes[ i ] ) );
+		nx = p.x; ny = p.y; nz = p.z; d = p.w;
+	}
 	__device__ __forceinline__ void node( int32_t i, float & d, int32_t & c0, int32_t & c1, uint32_t & w ) const {
 		const uint4 r = __ldg( reinterpret_cast< const uint4 * >( &nodes[ i ] ) );
 		d = __uint_as_float( r.x ); c0 = ( int32_t ) r.y; c1 = ( int32_t ) r.z; w = r.w;
@@ -200,10 +216,11 @@ struct GlobalMap {
 
 __device__ __forceinline__ void bind_global( const TraceParams & p, GlobalMap & g ) {
 	g.nodes = reinterpret_cast< const NodeRec * >( p.image );
-	g.gplanes = reinterpret_cast< const PlaneRec * >( p.image + p.off_gplanes );
-	g.refs = reinterpret_cast< const BrushRef * >( p.image + p.off_refs );
-	g.side_pairs = reinterpret_cast< const SideRec * >( p.image + p.off_side_pairs );
+	g.gplanes = p.g_gplanes;
+	g.refs = p.g_refs;
+	g.side_pairs = p.g_side_pairs;
 	g.node_orig = nullptr;
+	g.slot_pairs = p.g_slot_pairs;
 }
 
 #ifdef BSPGPU_EXPERIMENTS
@@ -359,6 +376,126 @@ __device__ __forceinline__ void stack_get( const SmemStack< kSlots, kStride > & 
 			: "r"( s.base + ( uint32_t ) i * ( uint32_t ) kStride ) : "memory" );
 	}
 	else stack_get( s.overflow, i, node, tmin, tmax );
+}
+
+/* the slot walk's entries {x, a, tmin, tmax}: all four words carry data */
+template< int kSlots, int kThreads > struct SlotStackOf { typedef SmemStack< kSlots, kThreads * 16 > type; };
+template< int kThreads > struct SlotStackOf< 0, kThreads > { typedef SlotEntry * type; };
+template< int kSlots, int kStride >
+__device__ __forceinline__ void sstack_put( const SmemStack< kSlots, kStride > & s, int32_t i, uint32_t x, uint32_t a, float tmin, float tmax ) {
+	asm volatile( "{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %0, %7;\n\t@q st.shared.v4.b32 [%1], {%3,%4,%5,%6};\n\t@!q st.local.v4.b32 [%2], {%3,%4,%5,%6};\n\t}"
+		:: "r"( i ), "r"( s.base + ( uint32_t ) i * ( uint32_t ) kStride ), "l"( __cvta_generic_to_local( reinterpret_cast< SlotEntry * >( s.overflow ) + i ) ),
+		   "r"( x ), "r"( a ), "f"( tmin ), "f"( tmax ), "n"( kSlots ) : "memory" );
+}
+template< int kSlots, int kStride >
+__device__ __forceinline__ void sstack_get( const SmemStack< kSlots, kStride > & s, int32_t i, uint32_t & x, uint32_t & a, float & tmin, float & tmax ) {
+	if( i < kSlots ) {
+		asm volatile( "ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"( x ), "=r"( a ), "=f"( tmin ), "=f"( tmax )
+			: "r"( s.base + ( uint32_t ) i * ( uint32_t ) kStride ) : "memory" );
+	}
+	else sstack_get( reinterpret_cast< const SlotEntry * >( s.overflow ), i, x, a, tmin, tmax );
+}
+
+/* read segment `sidx` and begin its slot walk (see lane_load_segment) */
+__device__ __forceinline__ bool slane_load_segment( const TraceParams & p, uint32_t sidx, LaneS & l ) {
+	float sx, sy, sz, ex, ey, ez;
+	load_endpoints( p, sidx, sx, sy, sz, ex, ey, ez );
+	SlotGrid g; g.cells = p.grid_slots; g.d = p.grid.d;
+	const Slot start = grid_start_slot( g, p.root, sx, sy, sz, ex, ey, ez );
+	slane_start( l, sx, sy, sz, ex, ey, ez );
+	slane_start_at( l, start );
+	if( !ray_is_plain( l.r ) ) {
+		const unsigned long long k = atomicAdd( p.next + 1, 1ull );
+		if( k < kExoticCap ) p.exotic_list[ k ] = sidx;
+		l.cx = kSlotIdle;
+		return false;
+	}
+	return true;
+}
+
+/* ---------------------------------------------------------------- K1/K2 over child slots: the same scheduling as trace_phased
+ * below, lanes walk Slot pairs (trace_core.h: LaneS) */
+template< int kMode, int kStack, int kMaxThreads, int kMinBlocks, int kSmemSlots, bool kGeneral >
+__global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_slots( const __grid_constant__ TraceParams p ) {
+	extern __shared__ __align__( 128 ) unsigned char smem[];
+	__shared__ __align__( 8 ) uint64_t stage_bar;
+	/* the warp's claimed block of segments {next, end}: warp-uniform, touched only at a refill -- kept out of the register file */
+	__shared__ uint2 warp_blk[ kMaxThreads / 32 ];
+
+	typename MapOf< kMode, kGeneral >::type map;
+	stage_and_bind< kMode >( p, smem, &stage_bar, map );
+
+	const unsigned kFull = 0xffffffffu;
+	const uint32_t warp_slot = opaque_u32( smem_u32( &warp_blk[ threadIdx.x >> 5 ] ) );
+	asm volatile( "st.shared.v2.u32 [%0], {%1,%1};" :: "r"( warp_slot ), "r"( 0u ) : "memory" );
+	uint32_t refill_at = p.refill;          /* idle lanes that trigger a refill; 33 once the launch has no segments left */
+
+	LaneS l;
+	slane_start( l, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f );
+	l.ca = 0; l.cx = kSlotIdle;
+	SlotEntry stack_local[ kStack ];
+	typename SlotStackOf< kSmemSlots, kMaxThreads >::type stack;
+	if constexpr( kSmemSlots > 0 ) {
+		stack.base = opaque_u32( smem_u32( smem ) + ( ( p.staged_bytes + 127u ) & ~127u ) + threadIdx.x * 16u );
+		stack.overflow = reinterpret_cast< StackEntry16 * >( stack_local );
+	}
+	else stack = stack_local;
+	uint32_t seg = 0, my_hits = 0;
+
+	for( ;; ) {
+		/* ---- retire finished segments (also those the start grid resolved at load time: a segment inside an empty leaf) */
+		if( slane_done( l ) ) {
+			HitState h;
+			slane_hit_state( l, h );
+			store_result( p, seg, l.r, h, p.g_side_plane );
+			my_hits += ( uint32_t ) h.hit;
+			l.cx = kSlotIdle;
+		}
+
+		/* ---- warp-level work fetch + compaction */
+		const unsigned idle = __ballot_sync( kFull, slane_idle( l ) );
+		const unsigned n_idle = __popc( idle );
+		if( n_idle >= refill_at ) {
+			uint32_t blk_next, blk_end;
+			asm volatile( "ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"( blk_next ), "=r"( blk_end ) : "r"( warp_slot ) : "memory" );
+			if( blk_next == blk_end ) {
+				unsigned long long b = 0;
+				if( ( threadIdx.x & 31u ) == 0 ) b = atomicAdd( p.next, ( unsigned long long ) p.block_segs );
+				b = __shfl_sync( kFull, b, 0 );
+				if( b >= ( unsigned long long ) p.n ) refill_at = 33u;
+				else {
+					blk_next = ( uint32_t ) b;
+					blk_end = ( uint32_t ) min( b + ( unsigned long long ) p.block_segs, ( unsigned long long ) p.n );
+				}
+			}
+			if( refill_at <= 32u ) {
+				const uint32_t avail = blk_end - blk_next;
+				const uint32_t rank = __popc( idle & ( ( 1u << ( threadIdx.x & 31u ) ) - 1u ) );
+				if( slane_idle( l ) && rank < avail ) {
+					seg = blk_next + rank;
+					if( p.perm ) seg = __ldg( p.perm + seg );                       /* binned order (N4): results still land at the segment's own index */
+					slane_load_segment( p, seg, l );
+				}
+				blk_next += min( n_idle, avail );
+				/* every lane stores the same pair, so each reads back its own store: no warp barrier needed */
+				asm volatile( "st.shared.v2.u32 [%0], {%1,%2};" :: "r"( warp_slot ), "r"( blk_next ), "r"( blk_end ) : "memory" );
+			}
+		}
+
+		/* ---- pick the phase most lanes are waiting for */
+		const unsigned in_node = __ballot_sync( kFull, slane_in_node( l ) );
+		const unsigned in_leaf = __ballot_sync( kFull, slane_in_leaf( l ) );
+		if( ( in_node | in_leaf ) == 0u ) {
+			if( __ballot_sync( kFull, slane_done( l ) ) != 0u ) continue;       /* loaded and already finished: retire them first */
+			if( refill_at > 32u ) break;
+			continue;
+		}
+		if( in_node == 0u || ( uint32_t ) __popc( in_leaf ) >= p.leaf_threshold ) slane_leaf_phase( map, l, stack, p.side_steps );
+		else slane_node_phase( map, l, stack, p.max_steps );
+	}
+
+	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( kFull, my_hits, o );
+	if( ( threadIdx.x & 31u ) == 0 && my_hits ) atomicAdd( p.hits, ( unsigned long long ) my_hits );
 }
 
 /* ---------------------------------------------------------------- K1/K2, phase-scheduled
@@ -540,7 +677,7 @@ __global__ void leaf_kernel( const LeafParams p ) {
 	map.nodes = reinterpret_cast< const NodeRec * >( p.image );
 	map.gplanes = reinterpret_cast< const PlaneRec * >( p.image + p.off_gplanes );
 	map.node_orig = reinterpret_cast< const NodeOrig * >( p.image + p.off_node_orig );
-	map.refs = nullptr; map.side_pairs = nullptr;
+	map.refs = nullptr; map.side_pairs = nullptr; map.slot_pairs = nullptr;
 	const int32_t * leaf_cluster = reinterpret_cast< const int32_t * >( p.image + p.off_leaf_cluster );
 	for( uint64_t i = blockIdx.x * ( uint64_t ) blockDim.x + threadIdx.x; i < p.n; i += ( uint64_t ) gridDim.x * blockDim.x ) {
 		const float * q = p.pts + i * p.stride;

@@ -124,7 +124,8 @@ enum {
 	BSPGPU_OPT_MAX_STEPS = 7,       /* node steps a lane takes per node phase; 0 = per-variant default */
 	BSPGPU_OPT_BLOCK_SEGS = 8,      /* consecutive segments a warp claims per global atomic: 0 = default (256), else 32..65536
 	                                   (rounded up to a multiple of 32) */
-	BSPGPU_OPT_SCHEDULER = 9,       /* 0 = phase-scheduled lanes (the shipped kernel).  4 = one thread per segment, no scheduling
+	BSPGPU_OPT_SCHEDULER = 9,       /* 0 = phase-scheduled lanes (the shipped kernel).  1 = the same with the node-record walk of the SMEM variant
+	                                   on the GLOBAL variant too (experiments build only, for A/B runs).  4 = one thread per segment, no scheduling
 	                                   (experiments build only; the naive baseline).  5 = rays wait in CTA-wide shared-memory queues and
 	                                   warps specialise on node or leaf work (experiments build only: bit-identical, measured 30 % slower) */
 	BSPGPU_OPT_SIDE_STEPS = 10,     /* side steps a lane takes per leaf phase; one step clips two brush sides (default 3) */

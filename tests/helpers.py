@@ -106,6 +106,7 @@ class HostSim:
             lib.hostsim_layout.argtypes = [C.c_void_p, C.c_void_p]
             lib.hostsim_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
             lib.hostsim_trace_phased.argtypes = lib.hostsim_trace.argtypes + [C.c_uint32, C.c_uint32, C.c_int]
+            lib.hostsim_trace_slots.argtypes = lib.hostsim_trace_phased.argtypes
             lib.hostsim_leaf.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
             cls._lib = lib
         return cls._lib
@@ -131,7 +132,9 @@ class HostSim:
         return dict(zip(("nodes", "refs", "sides", "depth", "staged_bytes", "total_bytes", "grid_cells", "general_planes", "unused"),
                         (int(v) for v in out)))
 
-    def trace(self, segs, budgets=None, grid=False, split_sides=False, split_stack=False):
+    def trace(self, segs, budgets=None, grid=False, split_sides=False, split_stack=False, walk="slots"):
+        """budgets=None: trace_one (the simple form); else the resumable walk with those step budgets -- walk="slots": over child
+        slots, what the shipped kernels run; walk="nodes": over node records"""
         from bsp_b200.api import RESULT_DT
         segs = np.ascontiguousarray(segs, np.float32)
         res = np.zeros(len(segs), RESULT_DT)
@@ -139,7 +142,8 @@ class HostSim:
         if budgets is None:
             self.l.hostsim_trace(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data)
         else:
-            self.l.hostsim_trace_phased(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], (1 if grid else 0) | (2 if split_sides else 0) | (4 if split_stack else 0))
+            fn = self.l.hostsim_trace_slots if walk == "slots" else self.l.hostsim_trace_phased
+            fn(self.h, segs.ctypes.data, 8, 4, len(segs), res.ctypes.data, pos.ctypes.data, budgets[0], budgets[1], (1 if grid else 0) | (2 if split_sides else 0) | (4 if split_stack else 0))
         return res, pos
 
     def leaf(self, pts):

@@ -24,6 +24,8 @@ struct Sim {
 	ImageMapSplit split;
 	const uint32_t * side_plane;
 	StartGrid grid;
+	SlotGrid sgrid;
+	Slot root;
 };
 std::string g_err;
 }
@@ -34,6 +36,8 @@ struct CountingMap {
 	ImageMap m;
 	mutable uint64_t nodes = 0, refs = 0, sides = 0;
 	void node( int32_t i, float & d, int32_t & c0, int32_t & c1, uint32_t & w ) const { nodes++; m.node( i, d, c0, c1, w ); }
+	void pair( uint32_t p, uint32_t & a0, uint32_t & x0, uint32_t & a1, uint32_t & x1 ) const { nodes++; m.pair( p, a0, x0, a1, x1 ); }
+	void gplane_d( uint32_t i, float & nx, float & ny, float & nz, float & d ) const { nodes++; m.gplane_d( i, nx, ny, nz, d ); }
 	void gplane( uint32_t i, float & nx, float & ny, float & nz ) const { nodes++; m.gplane( i, nx, ny, nz ); }
 	void ref( uint32_t i, uint32_t & first, uint32_t & nraw, int32_t & brush ) const { refs++; m.ref( i, first, nraw, brush ); }
 	void side( uint32_t i, float & nx, float & ny, float & nz, float & d ) const { sides++; m.side( i, nx, ny, nz, d ); }
@@ -55,7 +59,7 @@ void hostsim_count( void * h, const float * segs, uint64_t stride, uint64_t end_
 		const float * b = a + end_off;
 		Ray r; HitState hs;
 		if( grid && grid_start_ref( s->grid, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ] ) != 0 ) below++;
-		trace_one_phased< CountingMap, 128 >( cm, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], 8, 8, r, hs, grid ? &s->grid : nullptr );
+		trace_one_slots< CountingMap, 128 >( cm, s->root, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], 8, 8, r, hs, grid ? &s->sgrid : nullptr );
 	}
 	out[ 0 ] = cm.nodes; out[ 1 ] = cm.refs; out[ 2 ] = cm.sides; out[ 3 ] = below;
 }
@@ -74,6 +78,10 @@ void * hostsim_create_opts( const bspgpu_map_desc * lumps, int flags, int64_t gr
 	s->view.refs = ( const BrushRef * ) ( img + l.off_refs );
 	s->view.side_pairs = ( const SideRec * ) ( img + l.off_side_pairs );
 	s->view.node_orig = ( const NodeOrig * ) ( img + l.off_node_orig );
+	s->view.slots = ( const Slot * ) ( img + l.off_slots );
+	s->root = l.root;
+	s->sgrid.d = l.grid;
+	s->sgrid.cells = l.grid.dim[ 0 ] ? ( const Slot * ) ( img + l.off_grid_slots ) : nullptr;
 	static_cast< ImageMap & >( s->split ) = s->view;
 	s->split.sides_even = ( const SideRec * ) ( img + l.off_sides_even );
 	s->split.sides_odd = ( const SideRec * ) ( img + l.off_sides_odd );
@@ -134,6 +142,28 @@ void hostsim_trace_phased( void * h, const float * segs, uint64_t stride, uint64
 		if( use_grid & 4 ) trace_one_phased< ImageMap, 128, 2 >( s->view, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
 		else if( use_grid & 2 ) trace_one_phased< ImageMapSplit, 128 >( s->split, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
 		else trace_one_phased< ImageMap, 128 >( s->view, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
+		if( out ) out[ i ] = make_result( hs, s->side_plane );
+		if( pos4 ) {
+			make_pos( r, hs, pos4[ 4 * i + 0 ], pos4[ 4 * i + 1 ], pos4[ 4 * i + 2 ] );
+			pos4[ 4 * i + 3 ] = hs.t;
+		}
+	}
+}
+
+/* the walk the shipped kernels run: over child slots (trace_core.h: LaneS); flags as hostsim_trace_phased's use_grid */
+void hostsim_trace_slots( void * h, const float * segs, uint64_t stride, uint64_t end_off, uint64_t n, ResultRec * out, float * pos4,
+                          uint32_t node_budget, uint32_t side_budget, int flags ) {
+	const Sim * s = ( const Sim * ) h;
+	for( uint64_t i = 0; i < n; i++ ) {
+		const float * a = segs + i * stride;
+		const float * b = a + end_off;
+		Ray r; HitState hs;
+		const uint32_t nb = node_budget ? node_budget : 1 + ( uint32_t ) ( i % 7 );
+		const uint32_t sb = side_budget ? side_budget : 1 + ( uint32_t ) ( ( i / 7 ) % 5 );
+		const SlotGrid * grid = ( flags & 1 ) ? &s->sgrid : nullptr;
+		if( flags & 4 ) trace_one_slots< ImageMap, 128, 2 >( s->view, s->root, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
+		else if( flags & 2 ) trace_one_slots< ImageMapSplit, 128 >( s->split, s->root, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
+		else trace_one_slots< ImageMap, 128 >( s->view, s->root, a[ 0 ], a[ 1 ], a[ 2 ], b[ 0 ], b[ 1 ], b[ 2 ], nb, sb, r, hs, grid );
 		if( out ) out[ i ] = make_result( hs, s->side_plane );
 		if( pos4 ) {
 			make_pos( r, hs, pos4[ 4 * i + 0 ], pos4[ 4 * i + 1 ], pos4[ 4 * i + 2 ] );

@@ -22,9 +22,11 @@ def test_core_matches_oracle(oracle_mod, maps, name):
     sim = HostSim(m)
     res, pos = sim.trace(segs)
     _check(res, pos, exp, exp_pos, f"{name} trace_one")
-    for budgets in ((0, 0), (1, 1), (1000, 1000), (3, 2)):     # (0,0) = per-segment varying budgets
-        res, pos = sim.trace(segs, budgets)
-        _check(res, pos, exp, exp_pos, f"{name} phased {budgets}")
+    # both resumable walks: over child slots (the GLOBAL-variant kernels) and over node records (the SMEM variant)
+    for walk in ("slots", "nodes"):
+        for budgets in ((0, 0), (1, 1), (1000, 1000), (3, 2)):     # (0,0) = per-segment varying budgets
+            res, pos = sim.trace(segs, budgets, walk=walk)
+            _check(res, pos, exp, exp_pos, f"{name} {walk} walk, budgets {budgets}")
 
 
 @pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "tilted"])
@@ -41,7 +43,8 @@ def test_core_matches_golden_reference_outputs_for_extreme_floats(name):
     from helpers import check_against_extreme_golden
     m, segs, hit, t, pos = load_golden(name)
     sim = HostSim(m)
-    for budgets, kw in ((None, {}), ((0, 0), {}), ((0, 0), {"split_sides": True, "split_stack": False}), ((0, 0), {"split_stack": True})):
+    for budgets, kw in ((None, {}), ((0, 0), {}), ((0, 0), {"walk": "nodes"}), ((0, 0), {"split_sides": True, "split_stack": False}), ((0, 0), {"split_stack": True}),
+                        ((0, 0), {"split_sides": True, "walk": "nodes"}), ((0, 0), {"split_stack": True, "walk": "nodes"})):
         res, p = sim.trace(segs, budgets, **kw)
         check_against_extreme_golden(res["flags"] & 1, res["t"], p[:, :3], hit, t, pos, f"{name} {budgets} {kw}")
 
@@ -139,8 +142,9 @@ def test_start_grid_is_bit_identical(oracle_mod, maps, name):
     segs = np.vstack((mixed_segments(m, 50_000, 30_000, 100_000, 4096), seggen.long_rays(77, 0, 150_000, lo, hi, 0.01, 8.0),
                       grid_adversarial_segments(m, 200_000)))
     exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
-    res, pos = sim.trace(segs, (0, 0), grid=True)
-    _check(res, pos, exp, exp_pos, f"{name} start grid")
+    for walk in ("slots", "nodes"):
+        res, pos = sim.trace(segs, (0, 0), grid=True, walk=walk)
+        _check(res, pos, exp, exp_pos, f"{name} start grid, {walk} walk")
 
 
 @pytest.mark.parametrize("name", ["kat0", "kat1", "rooms8", "city10k", "tilted", "mega200k"])
@@ -168,7 +172,8 @@ def test_axis_node_records_are_bit_identical(oracle_mod, maps, name):
     ok = np.isfinite(exp_pos).all(axis=1)           # NaN payloads of pos are not pinned (helpers.check_against_extreme_golden)
     general = HostSim(m, general_planes_only=True)
     assert general.layout()["general_planes"] == lay["nodes"]
-    for s_, grid, kw in ((sim, False, {}), (sim, True, {}), (sim, True, {"split_sides": True}), (general, True, {})):
+    for s_, grid, kw in ((sim, False, {}), (sim, True, {}), (sim, True, {"split_sides": True}), (general, True, {}),
+                         (sim, True, {"walk": "nodes"}), (sim, True, {"split_sides": True, "walk": "nodes"}), (general, True, {"walk": "nodes"})):
         res, pos = s_.trace(segs, (0, 0), grid=grid and lay["grid_cells"] > 0, **kw)
         assert np.array_equal(bits(res).reshape(-1, 4), bits(exp).reshape(-1, 4)), f"{name} grid {grid} {kw}"
         assert np.array_equal(bits(pos[ok, :3]), bits(exp_pos[ok])), f"{name} pos grid {grid} {kw}"
