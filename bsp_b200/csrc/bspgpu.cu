@@ -304,6 +304,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 	p.staged_bytes = h->cfg_staged; p.top_nodes = h->cfg_top_nodes;
 	p.refill = ( uint32_t ) h->opt_refill;
 	p.max_steps = ( uint32_t ) ( h->opt_max_steps < 1 ? ( mode == kSmemAll ? 16 : 8 ) : h->opt_max_steps );
+	p.max_steps_long = ( uint32_t ) ( h->opt_max_steps < 1 ? 10 : h->opt_max_steps );   /* GLOBAL variant, warps whose segments start at the root */
 	p.side_steps = ( uint32_t ) h->opt_side_steps;
 	p.leaf_threshold = ( uint32_t ) h->opt_leaf_threshold;
 	p.hits = h->d_counters;
@@ -934,7 +935,14 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 			/* a claim of zero segments would let a warp spin on the work counter for ever */
 			if( value != 0 && ( value < 32 || value > 65536 ) ) return fail( BSPGPU_E_INVALID, "block segments must be 0 (default) or 32..65536" );
 			h->opt_block_segs = value == 0 ? 256 : ( value + 31 ) / 32 * 32; break;
-		case BSPGPU_OPT_SCHEDULER: if( value != 0 && value != 1 && value != 4 && value != 5 ) return fail( BSPGPU_E_INVALID, "scheduler must be 0 (or 1 / 4 / 5 in an experiments build)" ); h->opt_sched = value; break;
+		case BSPGPU_OPT_SCHEDULER: {
+#ifdef BSPGPU_EXPERIMENTS
+			const bool ab_walk = value == 1;
+#else
+			const bool ab_walk = false;
+#endif
+			if( value != 0 && !ab_walk && value != 4 && value != 5 ) return fail( BSPGPU_E_INVALID, "scheduler must be 0 (or 1 / 4 / 5 in an experiments build)" );
+		} h->opt_sched = value; break;
 		case BSPGPU_OPT_SIDE_STEPS: if( value < 1 || value > 1000000 ) return fail( BSPGPU_E_INVALID, "side steps must be 1..1000000" ); h->opt_side_steps = value; break;
 		case BSPGPU_OPT_LEAF_THRESHOLD: if( value < 1 || value > 32 ) return fail( BSPGPU_E_INVALID, "leaf threshold must be 1..32" ); h->opt_leaf_threshold = value; break;
 		case BSPGPU_OPT_SMEM_STACK: if( value < -1 || value > 8 ) return fail( BSPGPU_E_INVALID, "smem stack slots must be -1 (default), 0, 2, 4, 6 or 8" ); h->opt_smem_stack = value; break;

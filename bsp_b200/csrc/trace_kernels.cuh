@@ -68,6 +68,7 @@ struct TraceParams {
 	const uint4 * g_slot_pairs; const PlaneRec * g_gplanes; const BrushRef * g_refs; const SideRec * g_side_pairs; const uint32_t * g_side_plane;
 	Slot root;                        /* slot of node 0 */
 	const Slot * grid_slots;          /* start grid as slots, or null */
+	uint32_t max_steps_long;          /* node steps per phase while the warp's segments start at the root (long rays); max_steps otherwise */
 	unsigned long long * next;        /* work counter, zeroed before launch; next[1] counts the segments left to trace_exotic_kernel */
 	uint32_t * exotic_list;           /* the first kExoticCap of those segments' indices (beyond that the follow-up kernel rescans the launch) */
 	unsigned long long * hits;        /* accumulated hit count */
@@ -429,6 +430,7 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_slots( const 
 	const uint32_t warp_slot = opaque_u32( smem_u32( &warp_blk[ threadIdx.x >> 5 ] ) );
 	asm volatile( "st.shared.v2.u32 [%0], {%1,%1};" :: "r"( warp_slot ), "r"( 0u ) : "memory" );
 	uint32_t refill_at = p.refill;          /* idle lanes that trigger a refill; 33 once the launch has no segments left */
+	bool long_mode = true;                  /* scheduling follows the kind of segments the warp drew last (see the refill) */
 
 	LaneS l;
 	slane_start( l, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f );
@@ -471,11 +473,18 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_slots( const 
 			if( refill_at <= 32u ) {
 				const uint32_t avail = blk_end - blk_next;
 				const uint32_t rank = __popc( idle & ( ( 1u << ( threadIdx.x & 31u ) ) - 1u ) );
-				if( slane_idle( l ) && rank < avail ) {
+				const bool take = slane_idle( l ) && rank < avail;
+				if( take ) {
 					seg = blk_next + rank;
 					if( p.perm ) seg = __ldg( p.perm + seg );                       /* binned order (N4): results still land at the segment's own index */
 					slane_load_segment( p, seg, l );
 				}
+				/* what kind of batch is this?  Segments the start grid placed below the root are short moves: a few node steps
+				 * each, so long node phases run half empty and waiting leaf work should go first; segments that start at the
+				 * root are long rays, where the opposite holds (measured: profiles/README.md).  The warp follows the majority
+				 * of the segments it has just drawn; results do not depend on it. */
+				const unsigned at_root = __ballot_sync( kFull, take && l.cx == p.root.x && l.ca == p.root.a );
+				long_mode = 4u * __popc( at_root ) >= 3u * min( n_idle, avail );
 				blk_next += min( n_idle, avail );
 				/* every lane stores the same pair, so each reads back its own store: no warp barrier needed */
 				asm volatile( "st.shared.v2.u32 [%0], {%1,%2};" :: "r"( warp_slot ), "r"( blk_next ), "r"( blk_end ) : "memory" );
@@ -490,8 +499,10 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_slots( const 
 			if( refill_at > 32u ) break;
 			continue;
 		}
-		if( in_node == 0u || ( uint32_t ) __popc( in_leaf ) >= p.leaf_threshold ) slane_leaf_phase( map, l, stack, p.side_steps );
-		else slane_node_phase( map, l, stack, p.max_steps );
+		const uint32_t n_leaf = __popc( in_leaf );
+		const bool leaf_first = long_mode ? n_leaf >= p.leaf_threshold : 2u * n_leaf >= ( uint32_t ) __popc( in_node );
+		if( in_node == 0u || leaf_first ) slane_leaf_phase( map, l, stack, p.side_steps );
+		else slane_node_phase( map, l, stack, long_mode ? p.max_steps_long : p.max_steps );
 	}
 
 	for( int o = 16; o > 0; o >>= 1 ) my_hits += __shfl_xor_sync( kFull, my_hits, o );
