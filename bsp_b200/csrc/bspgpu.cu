@@ -350,7 +350,7 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 		/* rays the axis shortcut does not cover (zero start coordinate, non-finite component): counted by the kernel above, traced
 		 * here; returns immediately when there were none */
 		uint64_t xgrid = ( cnt + 255 ) / 256;
-		if( xgrid > ( uint64_t ) h->sm_count * 8 ) xgrid = ( uint64_t ) h->sm_count * 8;
+		if( xgrid > ( uint64_t ) h->sm_count * 2 ) xgrid = ( uint64_t ) h->sm_count * 2;   /* grid-stride; almost always there is nothing to do */
 		trace_exotic_kernel<<< ( unsigned ) xgrid, 256, 0, st >>>( p );
 		CK( cudaGetLastError() );
 		h->last_grid = ( uint32_t ) grid;

@@ -19,7 +19,7 @@ def main():
     from tools import mapgen
     ap = argparse.ArgumentParser()
     ap.add_argument("--map", default="rooms8")
-    ap.add_argument("--kind", default="uniform", choices=["uniform", "long", "short"])
+    ap.add_argument("--kind", default="uniform", choices=["uniform", "long", "short", "camera"])
     ap.add_argument("--n", type=int, default=16 * 1024 * 1024)
     ap.add_argument("--variants", default="0")
     ap.add_argument("--threads", default="0")
@@ -48,6 +48,10 @@ def main():
         g.generate(segs, 0, a.n, 0, 2, lo, hi)
     elif a.kind == "long":
         g.generate(segs, 0, a.n, 1, 3, lo, hi, 0.25 * diag, diag)
+    elif a.kind == "camera":
+        from tools import seggen
+        views = seggen.make_views(4, 64, lo, hi)
+        g.generate(segs, 0, a.n, 2, 0, lo, hi, views=views, width=3840, height=2160)
     else:
         g.generate(segs, 0, a.n, 1, 5, lo, hi, 1.0, 32.0)
     out = torch.empty((a.n, 4), dtype=torch.int32, device="cuda")
