@@ -358,7 +358,9 @@ BSPK_HD void lane_hit_state( const Lane & l, HitState & h ) {
 template< class Stack >
 BSPK_HD void lane_node_apply( Lane & l, const Stack & stack, float denom, float dist, int32_t c0, int32_t c1 ) {
 	const float u = dist / denom;                                                  /* :227 */
-	const bool in_range = denom != 0.0f && u >= 0.0f && u <= l.tmax;               /* :226,:232 */
+	/* :226,:232.  `denom != 0` is implied: a zero denominator makes u +-inf or NaN, and tmax is finite (1, or an earlier u that
+	 * passed this very test), so `u >= 0 && u <= tmax` already fails */
+	const bool in_range = u >= 0.0f && u <= l.tmax;
 	const bool below = u < l.tmin;                                                 /* :235 */
 	const bool both = in_range && !below;                                          /* :238 */
 	const bool near_back = ( dist > 0.0f ) != ( in_range && below );               /* :222,:236 */
@@ -389,8 +391,9 @@ BSPK_HD void lane_node_apply( Lane & l, const Stack & stack, float denom, float 
  * node step and the lane state spilled around it: measured -19 % on long rays). */
 BSPK_HD void ray_axis( const Ray & r, uint32_t w, float & s, float & d ) {
 #ifdef __CUDA_ARCH__
-	asm( "{\n\t.reg .pred p0, p1;\n\tsetp.eq.u32 p0, %2, 0;\n\tsetp.eq.u32 p1, %2, 1;\n\t"
-	     "selp.f32 %0, %4, %5, p1;\n\tselp.f32 %0, %3, %0, p0;\n\tselp.f32 %1, %7, %8, p1;\n\tselp.f32 %1, %6, %1, p0;\n\t}"
+	/* w is 0, 1 or 2: bit 0 <=> y, bit 1 <=> z (ptxas turns the two bit tests into one R2P) */
+	asm( "{\n\t.reg .pred p1, p2;\n\t.reg .b32 t1, t2;\n\tand.b32 t1, %2, 1;\n\tand.b32 t2, %2, 2;\n\tsetp.ne.u32 p1, t1, 0;\n\tsetp.ne.u32 p2, t2, 0;\n\t"
+	     "selp.f32 %0, %4, %3, p1;\n\tselp.f32 %0, %5, %0, p2;\n\tselp.f32 %1, %7, %6, p1;\n\tselp.f32 %1, %8, %1, p2;\n\t}"
 	     : "=&f"( s ), "=&f"( d ) : "r"( w ), "f"( r.sx ), "f"( r.sy ), "f"( r.sz ), "f"( r.dx ), "f"( r.dy ), "f"( r.dz ) );
 #else
 	s = w == 0u ? r.sx : ( w == 1u ? r.sy : r.sz );
