@@ -1,14 +1,20 @@
 /*
  * trace_kernels.cuh -- sm_100a kernels of the batched segment trace.
  *
- * trace_phased is persistent: each warp claims a private block of consecutive segments with one global atomicAdd
+ * Both trace kernels are persistent: each warp claims a private block of consecutive segments with one global atomicAdd
  * (warp-level work fetch) and re-fills lanes whose segment has finished from that block as soon as `refill` lanes
  * are idle (__ballot_sync / __popc ranks = the ray compaction), so a warp keeps ~32 live segments instead of waiting
- * for its slowest one.  Lanes are resumable node/leaf state machines (trace_core.h: Lane); each warp iteration runs
- * the one bounded phase most of its lanes wait for.  A node step is one 16-byte gather (split-plane distance, both
- * children, axis) + one plane test -- a second 16-byte gather only for the node planes that are not axis-aligned;
- * a leaf step is one 32-byte gather + two brush sides.  With the map in global memory the first traversal-stack
- * slots of every thread live in shared memory (SmemStack below).
+ * for its slowest one.  Lanes are resumable node/leaf state machines (trace_core.h); each warp iteration runs the one
+ * bounded phase most of its lanes wait for.  A leaf step is one 32-byte gather + two brush sides.
+ *
+ *   trace_slots  (GLOBAL variant: the map is read through L1/L2)  lanes walk CHILD SLOTS (map_layout.h: Slot): a node
+ *                step first asks for the 16-byte pair holding both children of its node, then runs the plane test on the
+ *                plane it already carries, then selects near / far -- the gather overlaps the IEEE division instead of
+ *                waiting for it (+4 % long rays, +9 % short moves on B200).  The first traversal-stack slots of every
+ *                thread live in shared memory (SmemStack below); the warp's scheduling policy follows the kind of
+ *                segments it drew last (short moves / long rays).
+ *   trace_phased (SMEM variant: the map is staged in shared memory; also the walk experiments builds can A/B)  lanes
+ *                walk node records: one 16-byte LDS per step (+ one for a node plane that is not axis-aligned).
  *
  * Map staging (template `kMode`):
  *   kSmemAll : the flattened map [nodes|gplanes|refs|sides_even|sides_odd] is copied into shared memory with
