@@ -47,6 +47,8 @@ WORKLOADS = {
     "rooms8-uniform": dict(map="rooms8", kind="uniform", seed=2),
     "mega200k-short": dict(map="mega200k", kind="long", seed=5, len_abs=(1.0, 32.0)),
     "city10k-camera": dict(map="city10k", kind="camera", seed=4, width=3840, height=2160, views=64),
+    # the same segments in a seeded random order ("also report a shuffled order for the divergence contrast")
+    "city10k-camera-shuffled": dict(map="city10k", kind="camera", seed=4, width=3840, height=2160, views=64, shuffle=True),
 }
 
 
@@ -90,6 +92,10 @@ def device_segments(g, w, buf, first, count):
     else:
         total = w["views"] * w["width"] * w["height"]
         g.generate(buf, first % total, count, 2, 0, w["lo"], w["hi"], views=w["view_array"], width=w["width"], height=w["height"])
+        if w.get("shuffle"):
+            import torch
+            gen = torch.Generator(device=buf.device); gen.manual_seed(w["seed"] + first)
+            buf.copy_(buf[torch.randperm(count, device=buf.device, generator=gen)])
 
 
 class ClockSampler:
@@ -636,7 +642,8 @@ def run_ours(a):
             line["cpu_baseline"] = cpu_line
 
     # ---- the other configurations of BASELINE.json, device-resident, same timing rules, each with its own parity sample:
-    #      C2 rooms8 (64 Mi uniform segments, map staged in shared memory), C4 camera grids on the city, C5 mega200k short moves.
+    #      C2 rooms8 (64 Mi uniform segments, map staged in shared memory), C4 camera grids on the city (row-major, and in a
+    #      shuffled order for the divergence contrast), C5 mega200k short moves.
     #      At N > 1 only C5 is repeated (BASELINE.json quotes it on 8 GPUs); the others are single-GPU configurations.
     also = [x for x in a.also.split(",") if x and x != a.workload]
     if world > 1:
@@ -676,7 +683,7 @@ def main():
     ap.add_argument("--segments-per-gpu", type=int, default=128 * 1024 * 1024)
     ap.add_argument("--e2e-segments", type=int, default=32 * 1024 * 1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--also", default="rooms8-uniform,city10k-camera,mega200k-short",
+    ap.add_argument("--also", default="rooms8-uniform,city10k-camera,city10k-camera-shuffled,mega200k-short",
                     help="other BASELINE.json configurations reported under 'also' (comma list, '' to skip); at N>1 only mega200k-short runs")
     ap.add_argument("--parity-rows", type=int, default=4096, help="rows of every rank's shard re-traced by the oracle port")
     ap.add_argument("--variant", type=int, default=None)
