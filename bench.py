@@ -529,11 +529,19 @@ def e2e_leg(g, w, a, local, rank, world, segs, out, barrier):
     if int((h_res8["bits"] & 1).sum()) != dev_hits_prefix or not np.array_equal(h_res8["t"][::stride].view(np.uint32), ref_rows[:, 0]) \
             or not np.array_equal(h_res8["bits"][::stride], ref_rows[:, 3] | ((ref_rows[:, 1] + 1) << 2)):
         raise SystemExit("bench.py: compact host-path results differ from device-path results")
+    h_t = h_out.reshape(-1)[:e2e_n].view(np.float32)
+    layouts["compact4"] = {"value": timed(lambda: g.trace(h_in, out=h_t, packed24=True, compact=4), e2e_steps), "h2d_bytes_per_step": e2e_n * 24, "d2h_bytes_per_step": e2e_n * 4}
+    # {hit, t} back from the 4-byte form: hit <=> value != T_MISS, t = value on a hit and 1 on a miss (the reference's own outputs)
+    hit4 = h_t != np.float32(bsp_b200.T_MISS)
+    t4 = np.where(hit4, h_t, np.float32(1.0)).astype(np.float32)
+    if int(hit4.sum()) != dev_hits_prefix or not np.array_equal(t4[::stride].view(np.uint32), ref_rows[:, 0]) or not np.array_equal(hit4[::stride], (ref_rows[:, 3] & 1) != 0):
+        raise SystemExit("bench.py: 4-byte host-path results differ from device-path results")
     best = max(layouts, key=lambda k: layouts[k]["value"])
     e2e = {"value": layouts[best]["value"], "unit": "traces/s", "h2d_bytes_per_step": layouts[best]["h2d_bytes_per_step"],
            "d2h_bytes_per_step": layouts[best]["d2h_bytes_per_step"], "layout": best, "layouts": layouts,
            "layout_note": "24 B packed vec3 pairs in (the reference's trace_seg arguments); out: result16 = 16-byte TraceResult {t, plane, brush, flags}, "
                           "compact8 = 8-byte bspgpu_result8 {t, flags | (plane+1) << 2} (BSPGPU_OUT_COMPACT8: everything the reference defines, hit and t, plus the plane extension); "
+                          "compact4 = one float, t on a hit and 2.0 on a miss (BSPGPU_OUT_COMPACT4: exactly the reference's outputs hit and t -- a hit has t <= 1 -- and pos is start + t * (end - start) from the caller's own segment); "
                           "pinned host memory, chunked 3-stream pipeline",
            "segments_per_gpu_per_step": e2e_n, "steps": e2e_steps}
     if rank == 0:

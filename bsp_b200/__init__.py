@@ -8,7 +8,7 @@ interface, ``csrc/host``).  This Python package is only the thin ctypes binding 
 CUDA library is missing or there is no sm_100 device, calls raise.
 """
 from .api import (  # noqa: F401
-    BspGpu, BspGpuError, RESULT_DT, RESULT8_DT, SEGMENT_FLOATS, HIT, STARTSOLID, lib_path, load_library, shard_range,
+    BspGpu, BspGpuError, RESULT_DT, RESULT8_DT, SEGMENT_FLOATS, HIT, STARTSOLID, T_MISS, lib_path, load_library, shard_range,
     VARIANT_AUTO, VARIANT_SMEM, VARIANT_TOPTREE, VARIANT_GLOBAL,
 )
 from .build import build  # noqa: F401

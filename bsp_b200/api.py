@@ -13,7 +13,8 @@ SEGMENT_FLOATS = 8
 HIT, STARTSOLID = 1, 2
 
 RESULT8_DT = np.dtype([("t", "<f4"), ("bits", "<u4")])      # bspgpu_result8: bits = flags | (plane + 1) << 2
-SEGS_DEVICE, OUT_DEVICE, SEGS_PACKED24, ASYNC, OUT_COMPACT8 = 1, 2, 4, 8, 16
+SEGS_DEVICE, OUT_DEVICE, SEGS_PACKED24, ASYNC, OUT_COMPACT8, OUT_COMPACT4 = 1, 2, 4, 8, 16, 32
+T_MISS = 2.0    # BSPGPU_T_MISS: what BSPGPU_OUT_COMPACT4 stores for a miss
 VARIANT_AUTO, VARIANT_SMEM, VARIANT_TOPTREE, VARIANT_GLOBAL = 0, 1, 2, 3
 OPT_VARIANT, OPT_BLOCK_THREADS, OPT_CTAS_PER_SM, OPT_TOPTREE_BYTES, OPT_CHUNK_SEGMENTS, OPT_REFILL, \
     OPT_MAX_STEPS, OPT_BLOCK_SEGS, OPT_SCHEDULER, OPT_SIDE_STEPS, OPT_LEAF_THRESHOLD, OPT_MAX_LAUNCH_SEGMENTS, OPT_START_GRID = range(1, 14)
@@ -208,7 +209,8 @@ class BspGpu:
     # -- the hot path
     def trace(self, segs, out=None, pos=None, n=None, packed24=False, async_=False, compact=False, stream=None):
         """segs: (n,8) float32 numpy array / torch tensor (host or cuda), or (n,6) with packed24.
-        out: RESULT_DT array or (n,4) int32/float32 tensor (compact: RESULT8_DT / (n,2)); allocated (numpy) when segs is a
+        out: RESULT_DT array or (n,4) int32/float32 tensor (compact=True or 8: RESULT8_DT / (n,2); compact=4: float32 (n,) -- t on a
+        hit, T_MISS = 2.0 on a miss, BSPGPU_OUT_COMPACT4); allocated (numpy) when segs is a
         numpy array and neither out nor pos is given.  Returns out (or pos when only pos was asked for).
         CUDA tensors: the call is enqueued on `stream` (a raw cudaStream_t) -- by default torch's CURRENT stream, so it is
         ordered after the kernels that produced `segs`; pass stream=False to use whatever bspgpu_set_stream installed."""
@@ -224,13 +226,13 @@ class BspGpu:
         if out is None and pos is None:
             if not isinstance(segs, np.ndarray):
                 raise ValueError("pass `out` for tensor inputs")
-            out = np.zeros(n, RESULT8_DT if compact else RESULT_DT)
-        for name, x, need in (("out", out, n * (8 if compact else 16)), ("pos", pos, n * 16)):
+            out = np.zeros(n, np.float32) if compact == 4 else np.zeros(n, RESULT8_DT if compact else RESULT_DT)
+        for name, x, need in (("out", out, n * (4 if compact == 4 else 8 if compact else 16)), ("pos", pos, n * 16)):
             if x is not None:
                 have = x.nbytes if isinstance(x, np.ndarray) else x.numel() * x.element_size()
                 if have < need:
                     raise ValueError(f"{name} holds {have} bytes, {need} needed for {n} segments")
-        flags = (SEGS_DEVICE if _is_device(segs) else 0) | (SEGS_PACKED24 if packed24 else 0) | (ASYNC if async_ else 0) | (OUT_COMPACT8 if compact else 0)
+        flags = (SEGS_DEVICE if _is_device(segs) else 0) | (SEGS_PACKED24 if packed24 else 0) | (ASYNC if async_ else 0) | (OUT_COMPACT4 if compact == 4 else OUT_COMPACT8 if compact else 0)
         outs_dev = [_is_device(x) for x in (out, pos) if x is not None]
         if any(outs_dev) and not all(outs_dev):
             raise ValueError("out and pos must both be host or both be device")

@@ -289,8 +289,8 @@ int configure( bspgpu * h ) {
 	return BSPGPU_OK;
 }
 
-/* results go to d_out (16-byte records) or, when `compact`, to the same pointer as 8-byte records */
-int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, void * d_out, bool compact, bspgpu_pos * d_pos, const uint32_t * d_perm, cudaStream_t st ) {
+/* results go to d_out as 16-byte records (compact 0), 8-byte records (1: BSPGPU_OUT_COMPACT8) or one float each (2: BSPGPU_OUT_COMPACT4) */
+int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, void * d_out, int compact, bspgpu_pos * d_pos, const uint32_t * d_perm, cudaStream_t st ) {
 	if( !h->cfg_valid ) { const int rc = configure( h ); if( rc != BSPGPU_OK ) return rc; }
 	TraceKernel kernel = h->cfg_kernel;
 	const int mode = h->cfg_mode, threads = h->cfg_threads;
@@ -341,8 +341,9 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 		const uint64_t base = d_perm ? 0 : done;
 		p.segs = packed24 ? nullptr : reinterpret_cast< const float4 * >( d_segs ) + base * 2;
 		p.segs24 = packed24 ? reinterpret_cast< const float2 * >( d_segs ) + base * 3 : nullptr;
-		p.out = ( d_out && !compact ) ? reinterpret_cast< ResultRec * >( d_out ) + base : nullptr;
-		p.out8 = ( d_out && compact ) ? reinterpret_cast< uint2 * >( d_out ) + base : nullptr;
+		p.out = ( d_out && compact == 0 ) ? reinterpret_cast< ResultRec * >( d_out ) + base : nullptr;
+		p.out8 = ( d_out && compact == 1 ) ? reinterpret_cast< uint2 * >( d_out ) + base : nullptr;
+		p.out4 = ( d_out && compact == 2 ) ? reinterpret_cast< float * >( d_out ) + base : nullptr;
 		p.pos = d_pos ? reinterpret_cast< float4 * >( d_pos ) + base : nullptr;
 		p.n = ( uint32_t ) cnt;
 		p.next = next;
@@ -445,9 +446,9 @@ int ensure_ring( bspgpu * h, size_t segs ) {
 	return BSPGPU_OK;
 }
 
-int trace_bounced( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_pos * pos, bool packed, bool compact, cudaStream_t st ) {
+int trace_bounced( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_pos * pos, bool packed, int compact, cudaStream_t st ) {
 	const size_t seg_bytes = packed ? 24 : sizeof( bspgpu_segment );
-	const size_t out_bytes = compact ? sizeof( bspgpu_result8 ) : sizeof( bspgpu_result );
+	const size_t out_bytes = compact == 2 ? sizeof( float ) : ( compact == 1 ? sizeof( bspgpu_result8 ) : sizeof( bspgpu_result ) );
 	uint64_t chunk = ( uint64_t ) h->opt_chunk;
 	if( chunk > n ) chunk = n;
 	{ const int rc = ensure_staging( h, ( size_t ) ( chunk < kSmallCall ? kSmallCall : chunk ), true, out != nullptr, pos != nullptr ); if( rc != BSPGPU_OK ) return rc; }
@@ -498,11 +499,13 @@ int trace_bounced( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu
 int trace_impl( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_pos * pos, unsigned flags, cudaStream_t st, bool foreign_stream ) {
 	if( n && ( !segs || ( !out && !pos ) ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: null segs, or both out and pos null" );
 	const bool segs_dev = ( flags & BSPGPU_SEGS_DEVICE ) != 0, out_dev = ( flags & BSPGPU_OUT_DEVICE ) != 0;
-	const bool packed = ( flags & BSPGPU_SEGS_PACKED24 ) != 0, compact = ( flags & BSPGPU_OUT_COMPACT8 ) != 0;
+	const bool packed = ( flags & BSPGPU_SEGS_PACKED24 ) != 0;
+	if( ( flags & BSPGPU_OUT_COMPACT8 ) && ( flags & BSPGPU_OUT_COMPACT4 ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: BSPGPU_OUT_COMPACT8 and BSPGPU_OUT_COMPACT4 exclude each other" );
+	const int compact = ( flags & BSPGPU_OUT_COMPACT4 ) ? 2 : ( ( flags & BSPGPU_OUT_COMPACT8 ) ? 1 : 0 );
 	if( ( flags & BSPGPU_ASYNC ) && !( segs_dev && out_dev ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: BSPGPU_ASYNC needs device pointers" );
 	/* the kernels read segments with 128-bit (packed: 64-bit) loads and write 16-byte (compact: 8-byte) records */
 	if( segs_dev && ( ( uintptr_t ) segs % ( packed ? 8 : 16 ) ) != 0 ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: device segments must be 16-byte aligned (8-byte for the packed layout)" );
-	if( out_dev && ( ( ( uintptr_t ) out % ( compact ? 8 : 16 ) ) != 0 || ( ( uintptr_t ) pos % 16 ) != 0 ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: device results must be 16-byte aligned (8-byte for compact records)" );
+	if( out_dev && ( ( ( uintptr_t ) out % ( compact == 2 ? 4 : ( compact == 1 ? 8 : 16 ) ) ) != 0 || ( ( uintptr_t ) pos % 16 ) != 0 ) ) return fail( BSPGPU_E_INVALID, "bspgpu_trace: device results must be 16-byte aligned (8-byte for compact records, 4-byte for BSPGPU_OUT_COMPACT4)" );
 	DeviceGuard guard( h->device );
 	/* work of an earlier call that went to a caller's stream shares this handle's counters and buffers: wait for it */
 	if( h->user_pending && !( foreign_stream && st == h->pending_stream ) ) { CK( cudaStreamWaitEvent( st, h->ev_user, 0 ) ); h->user_pending = false; }
@@ -511,7 +514,7 @@ int trace_impl( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_po
 	CK( cudaMemsetAsync( h->d_counters, 0, sizeof( unsigned long long ), st ) );
 	if( n == 0 ) return BSPGPU_OK;
 	const size_t seg_bytes = packed ? 24 : sizeof( bspgpu_segment );
-	const size_t out_bytes = compact ? sizeof( bspgpu_result8 ) : sizeof( bspgpu_result );
+	const size_t out_bytes = compact == 2 ? sizeof( float ) : ( compact == 1 ? sizeof( bspgpu_result8 ) : sizeof( bspgpu_result ) );
 
 	if( segs_dev && out_dev ) {
 		const uint32_t * d_perm = nullptr;

@@ -221,7 +221,7 @@ int bspgpu_multi_trace( bspgpu_multi_t * m, const void * segs, uint64_t n, bspgp
 	std::lock_guard< std::mutex > guard( m->lock );
 	const int w = world( m );
 	const size_t seg_bytes = ( flags & BSPGPU_SEGS_PACKED24 ) ? 24 : sizeof( bspgpu_segment );
-	const size_t out_bytes = ( flags & BSPGPU_OUT_COMPACT8 ) ? sizeof( bspgpu_result8 ) : sizeof( bspgpu_result );
+	const size_t out_bytes = ( flags & BSPGPU_OUT_COMPACT4 ) ? sizeof( float ) : ( ( flags & BSPGPU_OUT_COMPACT8 ) ? sizeof( bspgpu_result8 ) : sizeof( bspgpu_result ) );
 	/* a batch too small to be worth a thread per GPU runs on rank 0; the other ranks trace an empty shard so that their
 	 * hit counters read zero */
 	const uint32_t active = n < 16384ull * ( uint64_t ) w ? 1u : ( uint32_t ) w;

@@ -107,22 +107,40 @@ void BSP::trace_segs( const Segment * segs, size_t n, TraceResult * out ) const 
 }
 
 void BSP::trace_segs( const Segment * segs, size_t n, Intersection * is, bool * hit ) const {
-	/* a batch of one (trace_seg) or a handful: no heap traffic */
-	TraceResult res_small[ 16 ]; bspgpu_pos pos_small[ 16 ];
-	std::vector< TraceResult > res_big; std::vector< bspgpu_pos > pos_big;
-	TraceResult * res = res_small; bspgpu_pos * pos = pos_small;
-	if( n > 16 ) { res_big.resize( n ); pos_big.resize( n ); res = res_big.data(); pos = pos_big.data(); }
-	if( multi ) check( bspgpu_multi_trace( multi, segs, n, res, pos, BSPGPU_SEGS_PACKED24 ), "bspgpu_multi_trace" );
-	else check( bspgpu_trace_pos( gpu, segs, n, res, pos, BSPGPU_SEGS_PACKED24 ), "bspgpu_trace_pos" );
+	/* What the reference returns per segment is `hit` and `is.t`; `is.pos` is a function of those and of the caller's own
+	 * segment (bsp.cc:266).  So only 4 bytes per segment come back from the GPU (BSPGPU_OUT_COMPACT4: t, or BSPGPU_T_MISS) --
+	 * 8 with BSP_HOST_FILL_PLANE, for the plane index -- and pos is evaluated here, with the reference's own expression and one
+	 * rounding per operation (this file is built with -ffp-contract=off): bit-identical to the 16-byte position records.
+	 * A batch of one (trace_seg) or a handful: no heap traffic. */
+#ifdef BSP_HOST_FILL_PLANE
+	typedef bspgpu_result8 Wire;
+	const unsigned layout = BSPGPU_OUT_COMPACT8;
+#else
+	typedef float Wire;
+	const unsigned layout = BSPGPU_OUT_COMPACT4;
+#endif
+	Wire small[ 16 ];
+	std::vector< Wire > big;
+	Wire * w = small;
+	if( n > 16 ) { big.resize( n ); w = big.data(); }
+	if( multi ) check( bspgpu_multi_trace( multi, segs, n, reinterpret_cast< TraceResult * >( w ), nullptr, BSPGPU_SEGS_PACKED24 | layout ), "bspgpu_multi_trace" );
+	else check( bspgpu_trace( gpu, segs, n, reinterpret_cast< TraceResult * >( w ), BSPGPU_SEGS_PACKED24 | layout ), "bspgpu_trace" );
 	for( size_t i = 0; i < n; i++ ) {
 #ifdef BSP_HOST_FILL_PLANE
-		is[ i ].plane = res[ i ].plane >= 0 ? &planes[ res[ i ].plane ] : nullptr;
+		const bool h = ( w[ i ].bits & BSPGPU_HIT ) != 0;
+		const float t = w[ i ].t;
+		const int32_t plane = BSPGPU_RESULT8_PLANE( w[ i ].bits );
+		is[ i ].plane = plane >= 0 ? &planes[ plane ] : nullptr;
 #else
+		const bool h = w[ i ] != BSPGPU_T_MISS;
+		const float t = h ? w[ i ] : 1.0f;                         /* bis.is.t = 1.0f (bsp.cc:257) survives a miss */
 		is[ i ].plane = nullptr;                                   /* as the reference: never assigned */
 #endif
-		is[ i ].pos = glm::vec3( pos[ i ].pos[ 0 ], pos[ i ].pos[ 1 ], pos[ i ].pos[ 2 ] );
-		is[ i ].t = res[ i ].t;
-		if( hit ) hit[ i ] = ( res[ i ].flags & BSPGPU_HIT ) != 0;
+		const glm::vec3 & a = segs[ i ].start, & b = segs[ i ].end;
+		/* is.pos = start + is.t * ( end - start ) on a hit (bsp.cc:266), the zero-initialised (0,0,0) of `bis = { }` on a miss */
+		is[ i ].pos = h ? glm::vec3( a.x + t * ( b.x - a.x ), a.y + t * ( b.y - a.y ), a.z + t * ( b.z - a.z ) ) : glm::vec3( 0.0f, 0.0f, 0.0f );
+		is[ i ].t = t;
+		if( hit ) hit[ i ] = h;
 	}
 }
 

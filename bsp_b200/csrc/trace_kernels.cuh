@@ -61,6 +61,7 @@ struct TraceParams {
 	ResultRec * out;                  /* may be null */
 	float4 * pos;                     /* may be null */
 	uint2 * out8;                     /* may be null: compact results {t, flags | (plane+1) << 2} */
+	float * out4;                     /* may be null: t on a hit, 2.0f on a miss (BSPGPU_OUT_COMPACT4) */
 	uint32_t n;
 	uint32_t block_segs;              /* segments a warp claims per global atomic */
 	uint32_t refill;                  /* idle lanes that trigger a refill (1..32) */
@@ -320,6 +321,7 @@ __device__ __forceinline__ void store_result( const TraceParams & p, uint32_t se
 		const uint32_t packed = o.flags | ( ( uint32_t ) ( o.plane + 1 ) << 2 );
 		asm volatile( "st.global.cs.v2.b32 [%0], {%1,%2};" :: "l"( p.out8 + seg ), "r"( __float_as_uint( o.t ) ), "r"( packed ) : "memory" );
 	}
+	if( p.out4 ) asm volatile( "st.global.cs.f32 [%0], %1;" :: "l"( p.out4 + seg ), "f"( h.hit ? h.t : 2.0f ) : "memory" );
 	if( p.pos ) {
 		float px, py, pz;
 		make_pos( r, h, px, py, pz );                                   /* bsp.cc:265-267 */

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .api import BspGpuError, GenDesc, MapDesc, RESULT_DT, RESULT8_DT, OUT_COMPACT8, SEGS_PACKED24, load_library
+from .api import BspGpuError, GenDesc, MapDesc, RESULT_DT, RESULT8_DT, OUT_COMPACT8, OUT_COMPACT4, SEGS_PACKED24, load_library
 
 MULTI_SYMBOLS = (
     "bspgpu_multi_create", "bspgpu_multi_create_from_file", "bspgpu_multi_destroy", "bspgpu_multi_device_count", "bspgpu_multi_handle",
@@ -96,8 +96,8 @@ class BspGpuMulti:
             raise ValueError(f"segs must be a C-contiguous (n, {floats}) float32 numpy array")
         n = len(segs)
         if out is None and pos is None:
-            out = np.zeros(n, RESULT8_DT if compact else RESULT_DT)
-        flags = (SEGS_PACKED24 if packed24 else 0) | (OUT_COMPACT8 if compact else 0)
+            out = np.zeros(n, np.float32) if compact == 4 else np.zeros(n, RESULT8_DT if compact else RESULT_DT)
+        flags = (SEGS_PACKED24 if packed24 else 0) | (OUT_COMPACT4 if compact == 4 else OUT_COMPACT8 if compact else 0)
         _check(self.lib, self.lib.bspgpu_multi_trace(self.h, segs.ctypes.data, n, out.ctypes.data if out is not None else None,
                                                      pos.ctypes.data if pos is not None else None, flags))
         return out if out is not None else pos

@@ -104,6 +104,11 @@ typedef struct bspgpu_pos { float pos[ 3 ]; float t; } bspgpu_pos;
 #define BSPGPU_ASYNC         0x08u  /* device pointers only: enqueue on the handle's stream and return */
 #define BSPGPU_OUT_COMPACT8  0x10u  /* `out` points to 8-byte bspgpu_result8 records instead of 16-byte bspgpu_result (no `brush`):
                                        halves the device->host bytes of the host-pointer path */
+#define BSPGPU_OUT_COMPACT4  0x20u  /* `out` points to one float per segment: Intersection::t on a hit, BSPGPU_T_MISS on a miss -- exactly
+                                       what the reference returns (`hit`, `is.t`, bsp.cc:265-270; a hit has 0 <= t <= 1, never 2), in a
+                                       quarter of the bytes; `is.pos` is start + t * (end - start) (bsp.cc:266) from the caller's own
+                                       segment.  No extensions.  Device pointers must be 4-byte aligned. */
+#define BSPGPU_T_MISS 2.0f
 
 /* kernel variant override for bspgpu_set_option(BSPGPU_OPT_VARIANT): default AUTO */
 enum {

@@ -38,7 +38,7 @@ int bspgpu_multi_device_count( bspgpu_multi_t * m );
 /* the single-GPU handle of rank r (options, info, leaf queries); owned by `m` */
 bspgpu_t * bspgpu_multi_handle( bspgpu_multi_t * m, int rank );
 /* n x BSP::trace_seg over HOST arrays, sharded across the GPUs; out / pos as in bspgpu_trace_pos (either may be NULL);
- * flags: BSPGPU_SEGS_PACKED24, BSPGPU_OUT_COMPACT8.  Synchronous.  The hit counts of the shards are summed with
+ * flags: BSPGPU_SEGS_PACKED24, BSPGPU_OUT_COMPACT8 / BSPGPU_OUT_COMPACT4.  Synchronous.  The hit counts of the shards are summed with
  * ncclAllReduce (every GPU ends up with the total; bspgpu_multi_hit_count reads it). */
 int bspgpu_multi_trace( bspgpu_multi_t * m, const void * segs, uint64_t n, bspgpu_result * out, bspgpu_pos * pos, unsigned flags );
 int bspgpu_multi_hit_count( bspgpu_multi_t * m, uint64_t * hits );

@@ -59,6 +59,41 @@ int main( int argc, char ** argv ) {
 	if( bsp.last_hit_count() != hits ) { printf( "hit count %llu, want %llu\n", ( unsigned long long ) bsp.last_hit_count(), ( unsigned long long ) hits ); bad++; }
 	if( res[ 0 ].plane != -1 || !( res[ 10 ].flags & BSPGPU_STARTSOLID ) ) { printf( "extension fields off\n" ); bad++; }
 
+	/* the Intersection-shaped batch: only 4 bytes per segment come back from the GPU and `pos` is evaluated on the host with the
+	 * reference's expression (bsp_host.cc) -- it must carry the very bits of the device's 16-byte position records.  The KAT
+	 * segments plus 200 000 pseudo-random ones around the brushes (a batch well beyond the 16-segment stack buffers). */
+	{
+		std::vector< Segment > many( segs );
+		uint64_t x = 0x9e3779b97f4a7c15ull;
+		auto rnd = [ &x ]( float lo, float hi ) { x = x * 6364136223846793005ull + 1442695040888963407ull; return lo + ( hi - lo ) * ( float ) ( ( x >> 40 ) * ( 1.0 / 16777216.0 ) ); };
+		for( int i = 0; i < 200000; i++ ) {
+			Segment sg;
+			sg.start = glm::vec3( rnd( -80, 280 ), rnd( -40, 220 ), rnd( -30, 30 ) );
+			sg.end = glm::vec3( rnd( -80, 280 ), rnd( -40, 220 ), rnd( -30, 30 ) );
+			many.push_back( sg );
+		}
+		const size_t m = many.size();
+		std::vector< Intersection > is( m );
+		std::vector< uint8_t > hit8( m );
+		bsp.trace_segs( many.data(), m, is.data(), reinterpret_cast< bool * >( hit8.data() ) );
+		std::vector< TraceResult > r16( m );
+		std::vector< bspgpu_pos > p16( m );
+		const int rc = bsp.gpu ? bspgpu_trace_pos( bsp.gpu, many.data(), m, r16.data(), p16.data(), BSPGPU_SEGS_PACKED24 )
+		                       : bspgpu_multi_trace( bsp.multi, many.data(), m, r16.data(), p16.data(), BSPGPU_SEGS_PACKED24 );
+		if( rc != BSPGPU_OK ) { printf( "bspgpu_trace_pos: %s\n", bspgpu_last_error() ); bad++; }
+		size_t nhit = 0, diff = 0;
+		for( size_t i = 0; i < m; i++ ) {
+			const bool h = ( r16[ i ].flags & BSPGPU_HIT ) != 0;
+			nhit += h;
+			if( ( hit8[ i ] != 0 ) != h || bits( is[ i ].t ) != bits( r16[ i ].t ) || bits( is[ i ].pos.x ) != bits( p16[ i ].pos[ 0 ] ) ||
+			    bits( is[ i ].pos.y ) != bits( p16[ i ].pos[ 1 ] ) || bits( is[ i ].pos.z ) != bits( p16[ i ].pos[ 2 ] ) || is[ i ].plane != nullptr ) {
+				if( diff++ < 5 ) printf( "Intersection %zu differs from the 16-byte records: hit %d/%d t %08x/%08x\n", i, ( int ) hit8[ i ], ( int ) h, bits( is[ i ].t ), bits( r16[ i ].t ) );
+			}
+		}
+		if( diff ) { printf( "%zu of %zu Intersections differ\n", diff, m ); bad++; }
+		if( nhit < m / 50 || nhit > m - m / 50 ) { printf( "implausible hit count %zu of %zu\n", nhit, m ); bad++; }
+	}
+
 	/* position_to_leaf (bsp.cc:273-286): x<0 -> leaf 0; x>0,y>50 -> leaf 1; x>0,y<50 -> leaf 2 */
 	if( &bsp.position_to_leaf( glm::vec3( -5, 0, 0 ) ) != &bsp.leaves[ 0 ] ) { printf( "leaf 0\n" ); bad++; }
 	if( &bsp.position_to_leaf( glm::vec3( 5, 60, 0 ) ) != &bsp.leaves[ 1 ] ) { printf( "leaf 1\n" ); bad++; }

@@ -187,6 +187,21 @@ def test_compact_results_and_per_call_stream(native, maps, oracle_mod):
     d8 = torch.zeros((len(segs), 2), dtype=torch.int32, device="cuda")
     g.trace(d_segs, out=d8, compact=True)
     assert np.array_equal(d8.cpu().numpy().view(np.uint32), r8.view(np.uint32).reshape(-1, 2))
+    # BSPGPU_OUT_COMPACT4: one float per segment, t on a hit and T_MISS (2.0) on a miss -- {hit, t}, the reference's own outputs;
+    # host path (chunked, small, pageable), device path, both kernels, and the multi-chunk pinned path of the packed layout
+    want_t4 = np.where((exp["flags"] & 1) != 0, exp["t"], np.float32(native.T_MISS)).astype(np.float32)
+    for variant in (1, 3):
+        g.set_option(1, variant)
+        r4 = g.trace(segs, compact=4)
+        assert r4.dtype == np.float32 and np.array_equal(bits(r4), bits(want_t4)), f"compact4 variant {variant}"
+        assert np.array_equal(bits(g.trace(segs[:77], compact=4)), bits(want_t4[:77]))
+        d4 = torch.full((len(segs),), -1.0, dtype=torch.float32, device="cuda")
+        g.trace(d_segs, out=d4, compact=4)
+        assert np.array_equal(bits(d4.cpu().numpy()), bits(want_t4))
+        packed = np.ascontiguousarray(np.concatenate((segs[:, 0:3], segs[:, 4:7]), axis=1))
+        assert np.array_equal(bits(g.trace(packed, out=np.zeros(len(segs), np.float32), packed24=True, compact=4)), bits(want_t4))
+    g.set_option(1, 0)
+    assert ((r4 == np.float32(native.T_MISS)) == ((exp["flags"] & 1) == 0)).all() and (want_t4[(exp["flags"] & 1) != 0] <= 1.0).all()
     # ordering: fill the segments on a side stream, trace on that stream without any synchronisation in between
     side = torch.cuda.Stream()
     big = torch.from_numpy(np.tile(segs, (8, 1))).cuda()
