@@ -43,6 +43,10 @@ def test_multi_trace_host_arrays_against_the_reference(native, maps, oracle_mod)
         r8 = mg.trace(packed[:n], packed24=True, compact=True)
         assert np.array_equal(bits(r8["t"]), bits(exp["t"][:n])) and np.array_equal(r8["bits"] & 3, exp["flags"][:n])
         assert mg.hit_count() == int((exp["flags"][:n] & 1).sum())
+        # one float per segment (BSPGPU_OUT_COMPACT4): t on a hit, T_MISS on a miss; shards land at 4-byte offsets
+        r4 = mg.trace(packed[:n], packed24=True, compact=4)
+        hit = (exp["flags"][:n] & 1) != 0
+        assert r4.dtype == np.float32 and np.array_equal(bits(r4), bits(np.where(hit, exp["t"][:n], np.float32(native.T_MISS)).astype(np.float32)))
     mg.close()
 
 
