@@ -566,7 +566,8 @@ def e2e_leg(g, w, a, local, rank, world, segs, out, barrier):
                                        "chunk c+1 into and chunk c-2 out of the library's pinned ring while the GPU works on the chunks in between"}
         # small batches: BSP::trace_seg is a batch of one
         lat = {}
-        for n in (1, 1024, 65536):
+        for n, tiny in ((1, 1), (1, 0), (16, 1), (16, 0), (1024, 1), (65536, 1)):
+            g.set_option(18, tiny)                    # BSPGPU_OPT_TINY_CALLS: up to 16 host segments = one kernel over the pinned buffer
             s_in = np.array(h_in[:n]); s_out = np.zeros(n, bsp_b200.RESULT_DT)
             for _ in range(20):
                 g.trace(s_in, out=s_out, packed24=True)
@@ -574,7 +575,9 @@ def e2e_leg(g, w, a, local, rank, world, segs, out, barrier):
             t0 = time.perf_counter()
             for _ in range(reps):
                 g.trace(s_in, out=s_out, packed24=True)
-            lat[str(n)] = {"us_per_call": 1e6 * (time.perf_counter() - t0) / reps, "grid_ctas": g.info()["grid_ctas"]}
+            lat[str(n) if tiny else f"{n}_general_small_path"] = {"us_per_call": 1e6 * (time.perf_counter() - t0) / reps, "grid_ctas": g.info()["grid_ctas"]}
+        g.set_option(18, 1)
+        lat["note"] = "host arrays through bspgpu_trace from Python (ctypes call included); a batch of one is BSP::trace_seg, the reference's own call shape"
         e2e["latency"] = lat
         e2e["link_ceiling"] = link_probe()
         lc = e2e["link_ceiling"]

@@ -109,6 +109,7 @@ bool is_pageable_host( const void * ptr ) {
 	return a.type == cudaMemoryTypeUnregistered;
 }
 
+const uint64_t kTinyCall = kTinyRays;       /* host-pointer calls up to this many segments are ONE kernel over the pinned buffer (trace_tiny_kernel) */
 const uint64_t kSmallCall = 4096;           /* host-pointer calls up to this many segments go through one pinned bounce buffer on one stream */
 const uint64_t kPinThresholdBytes = 8ull << 20;
 
@@ -289,6 +290,22 @@ int configure( bspgpu * h ) {
 	return BSPGPU_OK;
 }
 
+/* the part of the kernel parameters that describes the map image */
+void map_params( bspgpu * h, TraceParams & p ) {
+	memset( &p, 0, sizeof( p ) );
+	p.image = h->d_image;
+	p.off_gplanes = h->lay.off_gplanes; p.off_refs = h->lay.off_refs; p.off_sides_even = h->lay.off_sides_even; p.off_sides_odd = h->lay.off_sides_odd;
+	p.off_side_pairs = h->lay.off_side_pairs; p.off_side_plane = h->lay.off_side_plane;
+	p.hits = h->d_counters;
+	p.grid.d = h->lay.grid;
+	p.off_slots = h->lay.off_slots; p.root = h->lay.root;
+	p.g_slot_pairs = reinterpret_cast< const uint4 * >( h->d_image + h->lay.off_slots );
+	p.g_gplanes = reinterpret_cast< const PlaneRec * >( h->d_image + h->lay.off_gplanes );
+	p.g_refs = reinterpret_cast< const BrushRef * >( h->d_image + h->lay.off_refs );
+	p.g_side_pairs = reinterpret_cast< const SideRec * >( h->d_image + h->lay.off_side_pairs );
+	p.g_side_plane = reinterpret_cast< const uint32_t * >( h->d_image + h->lay.off_side_plane );
+}
+
 /* results go to d_out as 16-byte records (compact 0), 8-byte records (1: BSPGPU_OUT_COMPACT8) or one float each (2: BSPGPU_OUT_COMPACT4) */
 int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, void * d_out, int compact, bspgpu_pos * d_pos, const uint32_t * d_perm, cudaStream_t st ) {
 	if( !h->cfg_valid ) { const int rc = configure( h ); if( rc != BSPGPU_OK ) return rc; }
@@ -297,26 +314,15 @@ int enqueue_trace( bspgpu * h, const void * d_segs, bool packed24, uint64_t n, v
 	const uint32_t smem = h->cfg_smem;
 
 	TraceParams p;
-	memset( &p, 0, sizeof( p ) );
-	p.image = h->d_image;
-	p.off_gplanes = h->lay.off_gplanes; p.off_refs = h->lay.off_refs; p.off_sides_even = h->lay.off_sides_even; p.off_sides_odd = h->lay.off_sides_odd;
-	p.off_side_pairs = h->lay.off_side_pairs; p.off_side_plane = h->lay.off_side_plane;
+	map_params( h, p );
 	p.staged_bytes = h->cfg_staged; p.top_nodes = h->cfg_top_nodes;
 	p.refill = ( uint32_t ) h->opt_refill;
 	p.max_steps = ( uint32_t ) ( h->opt_max_steps < 1 ? ( mode == kSmemAll ? 16 : 8 ) : h->opt_max_steps );
 	p.max_steps_long = ( uint32_t ) ( h->opt_max_steps < 1 ? 10 : h->opt_max_steps );   /* GLOBAL variant, warps whose segments start at the root */
 	p.side_steps = ( uint32_t ) h->opt_side_steps;
 	p.leaf_threshold = ( uint32_t ) h->opt_leaf_threshold;
-	p.hits = h->d_counters;
 	p.exotic_list = h->d_exotic;
 	p.pool_overflow = reinterpret_cast< float4 * >( h->d_pool_ovf );
-	p.grid.d = h->lay.grid;
-	p.off_slots = h->lay.off_slots; p.root = h->lay.root;
-	p.g_slot_pairs = reinterpret_cast< const uint4 * >( h->d_image + h->lay.off_slots );
-	p.g_gplanes = reinterpret_cast< const PlaneRec * >( h->d_image + h->lay.off_gplanes );
-	p.g_refs = reinterpret_cast< const BrushRef * >( h->d_image + h->lay.off_refs );
-	p.g_side_pairs = reinterpret_cast< const SideRec * >( h->d_image + h->lay.off_side_pairs );
-	p.g_side_plane = reinterpret_cast< const uint32_t * >( h->d_image + h->lay.off_side_plane );
 	const bool use_grid = h->opt_start_grid < 0 ? mode != kSmemAll : h->opt_start_grid != 0;
 	p.grid.cells = ( use_grid && h->lay.grid.dim[ 0 ] ) ? reinterpret_cast< const int32_t * >( h->d_image + h->lay.off_grid ) : nullptr;
 	p.grid_slots = p.grid.cells ? reinterpret_cast< const Slot * >( h->d_image + h->lay.off_grid_slots ) : nullptr;
@@ -511,6 +517,32 @@ int trace_impl( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_po
 	if( h->user_pending && !( foreign_stream && st == h->pending_stream ) ) { CK( cudaStreamWaitEvent( st, h->ev_user, 0 ) ); h->user_pending = false; }
 	h->last_launches = 0;
 	h->timing_valid = false; h->prepass_valid = false;
+
+	/* ---- a handful of host segments (a batch of one = BSP::trace_seg, the reference's only call shape): ONE kernel that reads
+	 *      the segments from and writes the results to the pinned buffer over the link, stores the hit count, and nothing else
+	 *      on the stream (trace_kernels.cuh: trace_tiny_kernel) */
+	if( n > 0 && n <= kTinyCall && !segs_dev && !out_dev && h->opt_tiny ) {
+		unsigned char * hs = h->h_small, * ho = hs + kSmallCall * 32, * hp = ho + kSmallCall * 16;
+		memcpy( hs, segs, n * ( packed ? 24 : sizeof( bspgpu_segment ) ) );
+		TraceParams p;
+		map_params( h, p );
+		p.segs = packed ? nullptr : reinterpret_cast< const float4 * >( hs );
+		p.segs24 = packed ? reinterpret_cast< const float2 * >( hs ) : nullptr;
+		p.out = ( out && compact == 0 ) ? reinterpret_cast< ResultRec * >( ho ) : nullptr;
+		p.out8 = ( out && compact == 1 ) ? reinterpret_cast< uint2 * >( ho ) : nullptr;
+		p.out4 = ( out && compact == 2 ) ? reinterpret_cast< float * >( ho ) : nullptr;
+		p.pos = pos ? reinterpret_cast< float4 * >( hp ) : nullptr;
+		p.n = ( uint32_t ) n;
+		trace_tiny_kernel<<< 1, ( unsigned ) n * 32u, 0, st >>>( p );
+		CK( cudaGetLastError() );
+		CK( cudaStreamSynchronize( st ) );
+		const size_t ob = compact == 2 ? sizeof( float ) : ( compact == 1 ? sizeof( bspgpu_result8 ) : sizeof( bspgpu_result ) );
+		if( out ) memcpy( out, ho, n * ob );
+		if( pos ) memcpy( pos, hp, n * sizeof( bspgpu_pos ) );
+		h->last_variant = BSPGPU_VARIANT_GLOBAL; h->last_threads = ( uint32_t ) n * 32u; h->last_smem = 0; h->last_slots = 0; h->last_grid = 1; h->last_launches = 1;
+		return BSPGPU_OK;
+	}
+
 	CK( cudaMemsetAsync( h->d_counters, 0, sizeof( unsigned long long ), st ) );
 	if( n == 0 ) return BSPGPU_OK;
 	const size_t seg_bytes = packed ? 24 : sizeof( bspgpu_segment );
@@ -951,6 +983,7 @@ int bspgpu_set_option( bspgpu_t * h, int option, int64_t value ) {
 		case BSPGPU_OPT_SMEM_STACK: if( value < -1 || value > 8 ) return fail( BSPGPU_E_INVALID, "smem stack slots must be -1 (default), 0, 2, 4, 6 or 8" ); h->opt_smem_stack = value; break;
 		case BSPGPU_OPT_START_GRID: h->opt_start_grid = value < 0 ? -1 : ( value ? 1 : 0 ); break;
 		case BSPGPU_OPT_BIN_SEGMENTS: h->opt_bin = value > 0 ? 1 : 0; break;
+		case BSPGPU_OPT_TINY_CALLS: h->opt_tiny = value ? 1 : 0; break;
 		case BSPGPU_OPT_PAGEABLE: if( value < 0 || value > 2 ) return fail( BSPGPU_E_INVALID, "pageable mode must be 0, 1 or 2" ); h->opt_pageable = value; break;
 		case BSPGPU_OPT_MAX_LAUNCH_SEGMENTS:
 			if( value < 32 || ( uint64_t ) value > kMaxLaunchSegs ) return fail( BSPGPU_E_INVALID, "max launch segments must be in [32, 2^30]" );

@@ -77,7 +77,7 @@ struct bspgpu {
 	int64_t opt_variant = BSPGPU_VARIANT_AUTO, opt_threads = 0, opt_ctas = 0, opt_top_bytes = 16 * 1024;
 	int64_t opt_chunk = 2ll << 20, opt_refill = 8, opt_max_steps = 0, opt_block_segs = 256;
 	int64_t opt_sched = 0, opt_side_steps = 3, opt_leaf_threshold = 16;
-	int64_t opt_smem_stack = -1, opt_start_grid = -1, opt_bin = 0, opt_pageable = 2;
+	int64_t opt_smem_stack = -1, opt_start_grid = -1, opt_bin = 0, opt_pageable = 2, opt_tiny = 1;
 	uint64_t opt_max_launch = kMaxLaunchSegs;   /* segments per kernel launch (lowered by tests to exercise the multi-launch path) */
 
 	/* launch configuration, recomputed only after an option changed */

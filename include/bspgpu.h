@@ -144,6 +144,9 @@ enum {
 	BSPGPU_OPT_BIN_SEGMENTS = 16,   /* 1: device-pointer traces first counting-sort the segments by the start-grid cell of their start
 	                                   point (a coherence pre-pass) and trace in that order; results still land at each
 	                                   segment's own index.  0 (default) off: measured in profiles/README.md */
+	BSPGPU_OPT_TINY_CALLS = 18,     /* host-pointer calls of up to 16 segments (a batch of one = BSP::trace_seg) run as ONE kernel that reads the
+	                                   segments from and writes the results to the handle's pinned buffer over the link -- no copies, no
+	                                   second kernel: 1 (default) on, 0 = the general small-call path (one bounce buffer, one stream) */
 	BSPGPU_OPT_PAGEABLE = 17        /* host-pointer calls with pageable (not page-locked) caller memory:
 	                                   2 (default) = bounce through the handle's pinned ring: host threads copy chunk c+1 in and
 	                                       chunk c-2 out while the GPU works on the chunks in between,

@@ -228,13 +228,33 @@ def test_small_batches_and_latency_path(native, maps, oracle_mod):
     assert len(segs) >= 4097
     exp, exp_pos, _ = oracle_mod.Port(m).trace(segs)
     g = native.BspGpu(m)
-    for n in (1, 2, 33, 1000, 4096, 4097):
-        pos = np.zeros((n, 4), np.float32)
-        res = g.trace(segs[:n], out=np.zeros(n, native.RESULT_DT), pos=pos)
-        _compare(res, pos, exp[:n], exp_pos[:n], f"small batch {n}")
-        assert g.hit_count() == int((exp["flags"][:n] & 1).sum())
-        if n <= 4096:
-            assert g.info()["grid_ctas"] <= -(-n // 32)
+    for tiny in (1, 0):
+        g.set_option(18, tiny)                       # BSPGPU_OPT_TINY_CALLS: up to 16 host segments are ONE kernel over the pinned buffer
+        for n in (1, 2, 16, 17, 33, 1000, 4096, 4097):
+            pos = np.zeros((n, 4), np.float32)
+            res = g.trace(segs[:n], out=np.zeros(n, native.RESULT_DT), pos=pos)
+            _compare(res, pos, exp[:n], exp_pos[:n], f"small batch {n} tiny {tiny}")
+            assert g.hit_count() == int((exp["flags"][:n] & 1).sum())
+            if n <= 4096:
+                assert g.info()["grid_ctas"] <= -(-n // 32)
+            if tiny and n <= 16:
+                assert g.info()["grid_ctas"] == 1 and g.info()["last_launches"] == 1
+    g.set_option(18, 1)
+    # the tiny path in every layout: packed segments, 8- and 4-byte results, positions only; extreme coordinates too
+    for n in (1, 7, 16):
+        packed = np.ascontiguousarray(np.concatenate((segs[:n, 0:3], segs[:n, 4:7]), axis=1))
+        r8 = g.trace(packed, packed24=True, compact=True)
+        assert np.array_equal(bits(r8["t"]), bits(exp["t"][:n])) and np.array_equal(r8["bits"], exp["flags"][:n] | ((exp["plane"][:n] + 1).astype(np.uint32) << 2))
+        r4 = g.trace(packed, packed24=True, compact=4)
+        assert np.array_equal(bits(r4), bits(np.where((exp["flags"][:n] & 1) != 0, exp["t"][:n], np.float32(native.T_MISS)).astype(np.float32)))
+        pos = g.trace(segs[:n], pos=np.zeros((n, 4), np.float32))
+        assert np.array_equal(bits(pos[:, :3]), bits(exp_pos[:n]))
+    from helpers import extreme_segments
+    ext = extreme_segments(256, 2048)
+    with np.errstate(all="ignore"):
+        eexp, _, _ = oracle_mod.Port(m).trace(ext)
+    for k in range(0, len(ext), 16):
+        _compare(g.trace(ext[k:k + 16], out=np.zeros(16, native.RESULT_DT)), None, eexp[k:k + 16], None, "tiny path, extreme coordinates")
     g.close()
 
 
