@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -125,7 +126,9 @@ void BSP::trace_segs( const Segment * segs, size_t n, Intersection * is, bool * 
 	if( n > 16 ) { big.resize( n ); w = big.data(); }
 	if( multi ) check( bspgpu_multi_trace( multi, segs, n, reinterpret_cast< TraceResult * >( w ), nullptr, BSPGPU_SEGS_PACKED24 | layout ), "bspgpu_multi_trace" );
 	else check( bspgpu_trace( gpu, segs, n, reinterpret_cast< TraceResult * >( w ), BSPGPU_SEGS_PACKED24 | layout ), "bspgpu_trace" );
-	for( size_t i = 0; i < n; i++ ) {
+	/* unpacking is a streaming loop over 24 + 4 bytes in, 24 + 1 bytes out per segment: large batches split it over a few threads */
+	auto unpack = [ & ]( size_t lo, size_t hi ) {
+	for( size_t i = lo; i < hi; i++ ) {
 #ifdef BSP_HOST_FILL_PLANE
 		const bool h = ( w[ i ].bits & BSPGPU_HIT ) != 0;
 		const float t = w[ i ].t;
@@ -142,6 +145,17 @@ void BSP::trace_segs( const Segment * segs, size_t n, Intersection * is, bool * 
 		is[ i ].t = t;
 		if( hit ) hit[ i ] = h;
 	}
+	};
+	const unsigned hw = std::thread::hardware_concurrency();
+	const size_t workers = n >= ( size_t ) 1 << 20 ? ( hw >= 16 ? 8 : ( hw >= 4 ? hw / 2 : 1 ) ) : 1;
+	if( workers <= 1 ) { unpack( 0, n ); return; }
+	std::vector< std::thread > pool;
+	const size_t per = ( n + workers - 1 ) / workers;
+	for( size_t k = 0; k < workers; k++ ) {
+		const size_t lo = k * per, hi = lo + per < n ? lo + per : n;
+		if( lo < hi ) pool.emplace_back( unpack, lo, hi );
+	}
+	for( std::thread & t : pool ) t.join();
 }
 
 bool BSP::trace_seg( const glm::vec3 & start, const glm::vec3 & end, Intersection & is ) const {

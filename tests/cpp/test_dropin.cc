@@ -61,12 +61,12 @@ int main( int argc, char ** argv ) {
 
 	/* the Intersection-shaped batch: only 4 bytes per segment come back from the GPU and `pos` is evaluated on the host with the
 	 * reference's expression (bsp_host.cc) -- it must carry the very bits of the device's 16-byte position records.  The KAT
-	 * segments plus 200 000 pseudo-random ones around the brushes (a batch well beyond the 16-segment stack buffers). */
+	 * segments plus 1.2 million pseudo-random ones around the brushes (beyond the 16-segment stack buffers, and enough for the threaded unpacking). */
 	{
 		std::vector< Segment > many( segs );
 		uint64_t x = 0x9e3779b97f4a7c15ull;
 		auto rnd = [ &x ]( float lo, float hi ) { x = x * 6364136223846793005ull + 1442695040888963407ull; return lo + ( hi - lo ) * ( float ) ( ( x >> 40 ) * ( 1.0 / 16777216.0 ) ); };
-		for( int i = 0; i < 200000; i++ ) {
+		for( int i = 0; i < 1200000; i++ ) {
 			Segment sg;
 			sg.start = glm::vec3( rnd( -80, 280 ), rnd( -40, 220 ), rnd( -30, 30 ) );
 			sg.end = glm::vec3( rnd( -80, 280 ), rnd( -40, 220 ), rnd( -30, 30 ) );
