@@ -522,6 +522,8 @@ int trace_impl( bspgpu * h, const void * segs, uint64_t n, void * out, bspgpu_po
 	 *      the segments from and writes the results to the pinned buffer over the link, stores the hit count, and nothing else
 	 *      on the stream (trace_kernels.cuh: trace_tiny_kernel) */
 	if( n > 0 && n <= kTinyCall && !segs_dev && !out_dev && h->opt_tiny ) {
+		/* options that cannot be honoured (a variant that does not fit, a scheduler this build lacks) fail here as on every other path */
+		if( !h->cfg_valid ) { const int rc = configure( h ); if( rc != BSPGPU_OK ) return rc; }
 		unsigned char * hs = h->h_small, * ho = hs + kSmallCall * 32, * hp = ho + kSmallCall * 16;
 		memcpy( hs, segs, n * ( packed ? 24 : sizeof( bspgpu_segment ) ) );
 		TraceParams p;
