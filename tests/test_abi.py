@@ -109,3 +109,17 @@ def test_multi_create_fails_loudly_without_a_gpu(native, maps):
     _, path = maps("kat0")
     with pytest.raises(native.BspGpuError, match="no CUDA device"):
         multi.BspGpuMulti(path)
+
+
+def test_flag_and_option_values_match_the_header(native):
+    """the Python bindings spell the trace flags and the miss marker as numbers: they must be the header's"""
+    from bsp_b200 import api
+    text = open(os.path.join(ROOT, "include", "bspgpu.h")).read()
+    defs = {m.group(1): m.group(2) for m in re.finditer(r"#define\s+(BSPGPU_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+u|[0-9.]+f)", text)}
+    for name, val in (("BSPGPU_SEGS_DEVICE", api.SEGS_DEVICE), ("BSPGPU_OUT_DEVICE", api.OUT_DEVICE), ("BSPGPU_SEGS_PACKED24", api.SEGS_PACKED24),
+                      ("BSPGPU_ASYNC", api.ASYNC), ("BSPGPU_OUT_COMPACT8", api.OUT_COMPACT8), ("BSPGPU_OUT_COMPACT4", api.OUT_COMPACT4)):
+        assert int(defs[name].rstrip("u"), 16) == val, name
+    assert float(defs["BSPGPU_T_MISS"].rstrip("f")) == native.T_MISS == 2.0
+    enums = dict(re.findall(r"\b(BSPGPU_OPT_[A-Z_]+)\s*=\s*(\d+)", text))
+    assert enums["BSPGPU_OPT_TINY_CALLS"] == "18" and enums["BSPGPU_OPT_PAGEABLE"] == "17" and enums["BSPGPU_OPT_SMEM_STACK"] == "15"
+    assert len(set(enums.values())) == len(enums)                # no two options share a number
