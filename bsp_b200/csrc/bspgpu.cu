@@ -298,7 +298,7 @@ void map_params( bspgpu * h, TraceParams & p ) {
 	p.off_side_pairs = h->lay.off_side_pairs; p.off_side_plane = h->lay.off_side_plane;
 	p.hits = h->d_counters;
 	p.grid.d = h->lay.grid;
-	p.off_slots = h->lay.off_slots; p.root = h->lay.root;
+	p.root = h->lay.root;
 	p.g_slot_pairs = reinterpret_cast< const uint4 * >( h->d_image + h->lay.off_slots );
 	p.g_gplanes = reinterpret_cast< const PlaneRec * >( h->d_image + h->lay.off_gplanes );
 	p.g_refs = reinterpret_cast< const BrushRef * >( h->d_image + h->lay.off_refs );

@@ -533,7 +533,8 @@ BSPK_HD void trace_one_phased( const Map & map, float sx, float sy, float sz, fl
 }
 
 /* ------------------------------------------------------------------------------------------
- * The same resumable walk over CHILD SLOTS (map_layout.h: Slot) -- what the shipped kernels run.
+ * The same resumable walk over CHILD SLOTS (map_layout.h: Slot) -- what the GLOBAL-variant kernel (trace_slots) runs; the
+ * SMEM-variant kernel (trace_phased) runs the node-record walk above.
  *
  * A lane carries the slot it is visiting {ca, cx}: plane + where the children are for an internal node, first brush
  * reference for a leaf.  A node step first issues the 16-byte gather of the node's two child slots, then runs the plane

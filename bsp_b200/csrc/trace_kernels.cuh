@@ -69,9 +69,9 @@ struct TraceParams {
 	uint32_t side_steps;              /* side steps per lane per leaf phase */
 	uint32_t leaf_threshold;          /* lanes waiting in a leaf that make the warp run a leaf phase */
 	StartGrid grid;                   /* cells == null: every walk starts at node 0 */
-	uint64_t off_slots;               /* child slots (map_layout.h: Slot) */
-	/* the same sections as absolute pointers: under register pressure the compiler re-derives a base from the constant bank
-	 * inside the hot loops, and image + offset is five instructions where a pointer parameter is two */
+	/* sections as absolute pointers (g_slot_pairs: the child slots in pairs, map_layout.h: Slot): under register pressure the
+	 * compiler re-derives a base from the constant bank inside the hot loops, and image + offset is five instructions where a
+	 * pointer parameter is two */
 	const uint4 * g_slot_pairs; const PlaneRec * g_gplanes; const BrushRef * g_refs; const SideRec * g_side_pairs; const uint32_t * g_side_plane;
 	Slot root;                        /* slot of node 0 */
 	const Slot * grid_slots;          /* start grid as slots, or null */
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__( kMaxThreads, kMinBlocks ) trace_slots( const 
 	typename SlotStackOf< kSmemSlots, kMaxThreads >::type stack;
 	if constexpr( kSmemSlots > 0 ) {
 		stack.base = opaque_u32( smem_u32( smem ) + ( ( p.staged_bytes + 127u ) & ~127u ) + threadIdx.x * 16u );
-		stack.overflow = reinterpret_cast< StackEntry16 * >( stack_local );
+		stack.overflow = reinterpret_cast< StackEntry16 * >( stack_local );   /* SmemStack is shared with trace_phased; both entry types are 16 bytes */
 	}
 	else stack = stack_local;
 	uint32_t seg = 0, my_hits = 0;
